@@ -1,0 +1,188 @@
+/* libmfac -- C ABI of the B200-native meanflow_audio_codec hot path.
+ *
+ * Every entry point takes plain device pointers and sizes (no torch / jax types),
+ * launches asynchronously on the given CUDA stream (passed as void* so this header
+ * needs no CUDA include), does no host synchronisation, owns no caller memory and
+ * returns an int status (0 = ok, negative = error; never throws).  Constant tables
+ * (window, twiddles, cosine basis) are built in fp64 on the host once per (N, hop)
+ * and cached per device inside the library.
+ *
+ * "ref:" comments name the reference interface each function replaces
+ * (paths inside /root/reference/meanflow_audio_codec/).
+ */
+#ifndef MFAC_H_
+#define MFAC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MFAC_API __attribute__((visibility("default")))
+#else
+#define MFAC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFAC_SUCCESS 0
+#define MFAC_ERR_BAD_SHAPE (-1)    /* non-positive size, inconsistent dims */
+#define MFAC_ERR_UNSUPPORTED (-2)  /* configuration the kernels do not cover */
+#define MFAC_ERR_WORKSPACE (-3)    /* workspace pointer null or too small */
+#define MFAC_ERR_NULL (-4)         /* required pointer is null */
+#define MFAC_ERR_DRIVER (-5)       /* CUDA driver entry point unavailable */
+#define MFAC_ERR_NCCL (-6)         /* NCCL unavailable or returned an error */
+/* CUDA runtime errors are returned as -(1000 + cudaError_t). */
+
+MFAC_API int mfac_version(void);
+MFAC_API const char* mfac_status_string(int status);
+
+/* ------------------------------------------------------------------ MDCT / IMDCT
+ * ref: preprocessing/mdct.py:143-198 (mdct), :201-256 (imdct); direct-cosine branch
+ * :317-372 with framing :476-495 and overlap-add :517-540.  N = window_size
+ * (coefficients per frame, a frame is 2N samples), hop = hop_size. */
+
+/* ref: mdct.py:491  nf = 1 if T < N else (T - N) / hop + 1 */
+MFAC_API int64_t mfac_mdct_num_frames(int64_t T, int32_t N, int32_t hop);
+/* ref: mdct.py:513  L = (nf - 1) * hop + 2N */
+MFAC_API int64_t mfac_imdct_length(int64_t nf, int32_t N, int32_t hop);
+
+/* x[B, T] (row-major, fp32) -> X[B, nf, N].  Zero right-padding to (nf-1)*hop+2N is implicit. */
+MFAC_API int mfac_mdct_f32(const float* x, float* X, int64_t B, int64_t T, int32_t N, int32_t hop, void* stream);
+/* X[B, nf, N] -> y[B, (nf-1)*hop + 2N]. */
+MFAC_API int mfac_imdct_f32(const float* X, float* y, int64_t B, int64_t nf, int32_t N, int32_t hop, void* stream);
+
+/* Strided forms used for channel-interleaved audio [B, T, C] <-> tokens [B, nf, N*C]
+ * (ref: preprocessing/tokenization.py:73-129, mdct.py:602-611,672-693): sample s of clip b is
+ * x[b * x_clip_stride + s * x_elem_stride]; coefficient k of frame i is
+ * X[b * X_clip_stride + i * X_frame_stride + k].  Strides are in elements. */
+MFAC_API int mfac_mdct_strided_f32(const float* x, int64_t x_clip_stride, int64_t x_elem_stride, float* X,
+                          int64_t X_clip_stride, int64_t X_frame_stride, int64_t B, int64_t T, int32_t N,
+                          int32_t hop, void* stream);
+MFAC_API int mfac_imdct_strided_f32(const float* X, int64_t X_clip_stride, int64_t X_frame_stride, float* y,
+                           int64_t y_clip_stride, int64_t y_elem_stride, int64_t B, int64_t nf, int32_t N,
+                           int32_t hop, void* stream);
+
+/* ------------------------------------------------------------------ MLP velocity network
+ * ref: models/mlp_flow.py:125-230 (ConditionalFlow), :63-117 (block), :39-55 (encoder).
+ *
+ * Parameters are ONE flat fp32 device array in jax tree_flatten order of the Flax tree
+ * (blocks_0..blocks_{nb-1} in numeric order, then encoder; inside a block:
+ * conditioning_layer/dense1/{bias,kernel}, conditioning_layer/dense2/{bias,kernel},
+ * mlp/dense1/{bias,kernel}, mlp/dense2/{bias,kernel}); kernels are [in, out] row-major
+ * exactly as flax.linen.Dense stores them.  Gradients and AdamW moments use the same layout.
+ * The tensor-core GEMMs read a bf16 "shadow" of the kernels (mfac_mlp_cast_params, refreshed
+ * by mfac_adamw_step); biases are read from the fp32 array. */
+typedef struct MfacMlpDims {
+  int32_t D;  /* noise_dimension (tokens flattened: nf * N) */
+  int32_t L;  /* latent_dimension */
+  int32_t C;  /* condition_dimension (even) */
+  int32_t nb; /* num_blocks */
+} MfacMlpDims;
+
+enum MfacParamId {
+  MFAC_P_COND1_B = 0, MFAC_P_COND1_W = 1, MFAC_P_COND2_B = 2, MFAC_P_COND2_W = 3,
+  MFAC_P_MLP1_B = 4, MFAC_P_MLP1_W = 5, MFAC_P_MLP2_B = 6, MFAC_P_MLP2_W = 7,
+  /* encoder (block = -1) */
+  MFAC_P_ENC1_B = 0, MFAC_P_ENC1_W = 1, MFAC_P_ENC2_B = 2, MFAC_P_ENC2_W = 3
+};
+
+MFAC_API int64_t mfac_mlp_param_count(const MfacMlpDims* dims);
+/* Offset (elements) and shape of one leaf; block = -1 selects the encoder. rows = 1 for biases. */
+MFAC_API int mfac_mlp_param_offset(const MfacMlpDims* dims, int32_t block, int32_t which, int64_t* offset, int64_t* rows,
+                          int64_t* cols);
+MFAC_API size_t mfac_mlp_shadow_bytes(const MfacMlpDims* dims);
+MFAC_API int mfac_mlp_cast_params(const MfacMlpDims* dims, const float* params, void* shadow, void* stream);
+
+enum MfacWorkspaceKind {
+  MFAC_WS_FORWARD = 0, /* mfac_mlp_forward / mfac_mlp_encode */
+  MFAC_WS_LOSS_GRAD = 1, /* mfac_imf_loss_grad */
+  MFAC_WS_SAMPLE = 2     /* mfac_sample */
+};
+MFAC_API size_t mfac_workspace_bytes(int32_t kind, const MfacMlpDims* dims, int64_t B);
+
+/* ref: model.apply({"params": p}, x, method="encode")  (mlp_flow.py:153-162).  x[B,D] -> latents[B,L] */
+MFAC_API int mfac_mlp_encode(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x,
+                    float* latents, int64_t B, void* ws, size_t ws_bytes, void* stream);
+/* ref: model.apply({"params": p}, x, time, latents)  (mlp_flow.py:199-230).
+ * x[B,D], time[B,2] = (t,h), latents[B,L] or NULL (zeros, mlp_flow.py:223-228) -> out[B,D] */
+MFAC_API int mfac_mlp_forward(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x,
+                     const float* time, const float* latents, float* out, int64_t B, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------ iMF loss + gradients
+ * ref: ImprovedMeanFlowLoss.compute_loss (trainers/loss_strategies.py:227-280) with
+ * LinearNoiseSchedule (trainers/noise_schedules.py:69-88), sample_tr (utils.py:36-45) and
+ * weighted_l2_loss (utils.py:16-25).
+ *
+ * e[B,D], t[B], r[B] may be given explicitly (parity mode; the reference re-draws the same
+ * values every step) or all NULL, in which case they are drawn on the device
+ * from a Philox counter stream keyed by (seed, step, rank offset).  grads is the flat fp32
+ * gradient (same layout as params; overwritten).  loss is one fp32.  The optional outputs
+ * (any may be NULL) expose intermediates for parity tests. */
+typedef struct MfacImfConfig {
+  float noise_min, noise_max;          /* 0.001, 0.999 */
+  float time_mean, time_std;           /* -0.4, 1.0 */
+  float data_proportion;               /* 0.5 : first int(B*p) rows get r = t */
+  float loss_c;                        /* 1e-3 (p = 1) */
+  int32_t use_weighted_loss;           /* 1 */
+  uint64_t seed;
+  uint64_t step;
+  uint64_t row_offset;                 /* global index of local row 0 (rank * B) for the RNG */
+} MfacImfConfig;
+
+typedef struct MfacImfAux {
+  float* v;           /* [B,D] */
+  float* u;           /* [B,D] */
+  float* dudt;        /* [B,D] */
+  float* per_example; /* [B]  sum_d delta^2 */
+  float* e;           /* [B,D] noise actually used */
+  float* t;           /* [B] */
+  float* r;           /* [B] */
+} MfacImfAux;
+
+MFAC_API int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
+                       const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
+                       const MfacImfAux* aux, int64_t B, void* ws, size_t ws_bytes, void* stream);
+
+/* ref: optax.adamw(lr, weight_decay) + TrainState.apply_gradients
+ * (trainers/train.py:236, trainers/training_steps.py:33).  Decoupled decay on ALL leaves.
+ * count = steps already taken.  grad_scale multiplies the gradient first (1/world after a
+ * sum all-reduce).  If shadow != NULL the bf16 kernels are refreshed in the same pass. */
+MFAC_API int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
+                    int64_t count, float lr, float b1, float b2, float eps, float weight_decay, float grad_scale,
+                    void* stream);
+
+/* ------------------------------------------------------------------ samplers
+ * MFAC_SAMPLE_HEUN  ref: evaluators/sampling.py:5-95 (h = 0, grid linspace(1,0,n), dt = 1/n).
+ * MFAC_SAMPLE_MF    mean-flow few-step rule x_r = x_t - (t-r) u(x_t,[t,t-r]) on a uniform grid
+ *                   (documentation/research/improved_meanflow/improved_meanflow_key_eqn.md:311-318);
+ *                   n_steps = 1 or 2 are the 1-/2-NFE samplers.
+ * noise[B,D] may be NULL (Philox, keyed by seed).  latents[B,L] required (sampling.py:42-45). */
+enum MfacSampleMode { MFAC_SAMPLE_HEUN = 0, MFAC_SAMPLE_MF = 1 };
+MFAC_API int mfac_sample(const MfacMlpDims* dims, const float* params, const void* shadow, const float* latents,
+                const float* noise, int32_t mode, int32_t n_steps, float guidance_scale, uint64_t seed, float* out,
+                int64_t B, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ data-parallel gradient all-reduce
+ * (absent in the reference).  id_bytes = the 128-byte ncclUniqueId. */
+MFAC_API int mfac_comm_unique_id(void* id_bytes_out);
+MFAC_API int mfac_comm_init(const void* id_bytes, int32_t rank, int32_t world);
+MFAC_API int mfac_comm_allreduce_sum_f32(float* buf, int64_t count, void* stream);
+MFAC_API int mfac_comm_destroy(void);
+
+/* ------------------------------------------------------------------ test hooks
+ * C[M,N] fp32 = A * B with bf16 operands through the production tcgen05 GEMM.
+ * a_mn_major = 0: A stored [M,K] (K contiguous); 1: stored [K,M].
+ * b_mn_major = 0: B stored [N,K] (K contiguous); 1: stored [K,N]. */
+MFAC_API int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int64_t M, int64_t N, int64_t K,
+                         int32_t a_mn_major, int32_t b_mn_major, int32_t block_n, void* stream);
+/* 1 = route every GEMM through a plain SIMT kernel (debug triage only; never set in product use). */
+MFAC_API int mfac_debug_set_simt_gemm(int32_t on);
+MFAC_API int mfac_debug_counters(int64_t* kernel_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFAC_H_ */

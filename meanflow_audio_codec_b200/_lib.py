@@ -1,0 +1,121 @@
+"""ctypes binding of ``libmfac.so`` (the C ABI declared in ``include/mfac.h``).
+
+The product path has no fallback: if the shared library is missing or a CUDA device
+is absent when a compute entry point is called, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmfac.so"
+
+
+class MfacError(RuntimeError):
+    pass
+
+
+class MlpDims(C.Structure):
+    _fields_ = [("D", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("nb", C.c_int32)]
+
+
+class ImfConfig(C.Structure):
+    _fields_ = [
+        ("noise_min", C.c_float), ("noise_max", C.c_float),
+        ("time_mean", C.c_float), ("time_std", C.c_float),
+        ("data_proportion", C.c_float), ("loss_c", C.c_float),
+        ("use_weighted_loss", C.c_int32),
+        ("seed", C.c_uint64), ("step", C.c_uint64), ("row_offset", C.c_uint64),
+    ]
+
+
+class ImfAux(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("v", "u", "dudt", "per_example", "e", "t", "r")]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_F = C.c_float
+
+# name -> (restype, argtypes); mirrors include/mfac.h one to one
+PROTOTYPES = {
+    "mfac_version": (C.c_int, []),
+    "mfac_status_string": (C.c_char_p, [C.c_int]),
+    "mfac_mdct_num_frames": (_I64, [_I64, _I32, _I32]),
+    "mfac_imdct_length": (_I64, [_I64, _I32, _I32]),
+    "mfac_mdct_f32": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _P]),
+    "mfac_imdct_f32": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _P]),
+    "mfac_mdct_strided_f32": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P]),
+    "mfac_imdct_strided_f32": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P]),
+    "mfac_mlp_param_count": (_I64, [C.POINTER(MlpDims)]),
+    "mfac_mlp_param_offset": (C.c_int, [C.POINTER(MlpDims), _I32, _I32, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "mfac_mlp_shadow_bytes": (C.c_size_t, [C.POINTER(MlpDims)]),
+    "mfac_mlp_cast_params": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P]),
+    "mfac_workspace_bytes": (C.c_size_t, [_I32, C.POINTER(MlpDims), _I64]),
+    "mfac_mlp_encode": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I64, _P, C.c_size_t, _P]),
+    "mfac_mlp_forward": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _I64, _P, C.c_size_t, _P]),
+    "mfac_imf_loss_grad": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), _P, _P, _P, _P, _P, _P, _P, _P,
+                                     C.POINTER(ImfAux), _I64, _P, C.c_size_t, _P]),
+    "mfac_adamw_step": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
+    "mfac_sample": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I32, _I32, _F, C.c_uint64, _P, _I64, _P,
+                              C.c_size_t, _P]),
+    "mfac_comm_unique_id": (C.c_int, [_P]),
+    "mfac_comm_init": (C.c_int, [_P, _I32, _I32]),
+    "mfac_comm_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),
+    "mfac_comm_destroy": (C.c_int, []),
+    "mfac_debug_gemm_bf16": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
+    "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
+    "mfac_debug_counters": (C.c_int, [C.POINTER(_I64)]),
+}
+
+WS_FORWARD, WS_LOSS_GRAD, WS_SAMPLE = 0, 1, 2
+SAMPLE_HEUN, SAMPLE_MF = 0, 1
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load ``libmfac.so`` (once).  Raises MfacError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise MfacError(
+                f"{LIB_PATH} not found: build it with `python -m meanflow_audio_codec_b200.build` "
+                "(there is no CPU or PyTorch fallback)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().mfac_status_string(int(status)).decode()
+        raise MfacError(f"libmfac {what} failed: {msg} (status {status})")
+
+
+def launches() -> int:
+    n = _I64(0)
+    lib().mfac_debug_counters(C.byref(n))
+    return int(n.value)
+
+
+def require_cuda(t, name: str = "input"):
+    import torch
+
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device, got {type(t)}")
+    if not t.is_cuda:
+        raise MfacError(f"{name} must live on a CUDA device: libmfac has no CPU path")
+    return t
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,528 @@
+// MDCT analysis / IMDCT overlap-add synthesis for sm_100a.
+//
+// Reference semantics: the direct-cosine branch of preprocessing/mdct.py
+//   X[b,i,k] = sum_{n<2N} x[b, i*hop+n] w[n] cos(pi/N (n + N/2 + 1/2)(k + 1/2))        (mdct.py:317-327,347-358)
+//   y[b,s]   = sum_i (2/N) w[s-i*hop] sum_k X[b,i,k] cos(pi/N (s-i*hop + N/2 + 1/2)(k + 1/2))   (:330-340,361-372,517-540)
+// with w[n] = sin(pi (n+1/2) / 2N)  (:126-136), nf = 1 if T<N else (T-N)/hop+1, zero right padding (:487-494).
+//
+// Two code paths, both fp32 arithmetic with tables generated in fp64 on the host:
+//  * N == 512 (every shipped config): the 2N->N TDAC fold is fused with the window, the N-point
+//    DCT-IV is computed through one 256-point complex FFT per frame (pre/post twiddle), one warp per
+//    frame, 8-8-4 radix passes in registers with two padded shared-memory exchanges.  Frames of a
+//    clip share one staged input segment (framing costs no extra HBM traffic).  The inverse runs the
+//    same DCT-IV, keeps the N-sample core of each frame in shared memory and every output sample
+//    gathers its <= ceil(2N/hop) frames (unfold + window + 2/N) -- no scan, no atomics.
+//  * any other N: dense contraction against the cached windowed cosine basis (exactly the
+//    reference's einsum), tiled through shared memory.
+// HBM-bound: algorithmic bytes are 4*(T + nf*N) per clip forward, 4*(nf*N + L) inverse.
+#include <map>
+#include <mutex>
+#include <vector>
+#include <cmath>
+
+#include "mfac_common.cuh"
+
+namespace mfac {
+
+void count_launch();
+
+struct StridedIO {
+  int64_t in_clip_stride, in_elem_stride;    // MDCT: x ; IMDCT: X (elem stride = frame stride)
+  int64_t out_clip_stride, out_elem_stride;  // MDCT: X (elem stride = frame stride); IMDCT: y
+};
+
+namespace {
+
+constexpr int FFT_N = 512;       // window_size handled by the FFT path
+constexpr int FFT_H = 256;       // complex FFT length
+constexpr int SCR_STRIDE = 36;   // padded row stride (float2) of the per-warp exchange buffer
+constexpr int SCR_F2 = 8 * SCR_STRIDE;  // 288 float2 = 576 floats >= 512 staging floats
+constexpr int MDCT_WARPS = 8;
+
+struct FftTables {      // device pointers
+  const float* window;  // [2N]
+  const float2* pre;    // [H]   exp(-i pi (4m+1) / 4N)
+  const float2* post;   // [H]   exp(-i pi k / N)
+  const float2* w64;    // [64]  exp(-2 pi i q / 64)
+  const float2* w256;   // [256] exp(-2 pi i q / 256)
+};
+
+struct DenseTables {
+  const float* wc;   // [2N, N]  w[n] * C[n,k]
+  const float* wct;  // [N, 2N]  (2/N) * w[n] * C[n,k], transposed
+};
+
+struct TableSet {
+  FftTables fft{};
+  DenseTables dense{};
+  bool has_fft = false, has_dense = false;
+};
+
+std::mutex g_mu;
+std::map<std::pair<int, int>, TableSet> g_tables;  // (device, N)
+
+template <typename T>
+int upload(const std::vector<T>& h, const T** out) {
+  T* d = nullptr;
+  MFAC_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(T)));
+  MFAC_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return MFAC_SUCCESS;
+}
+
+int get_tables(int N, bool want_fft, TableSet* out) {
+  int dev = 0;
+  MFAC_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_mu);
+  TableSet& ts = g_tables[{dev, N}];
+  const double pi = 3.14159265358979323846;
+  if (want_fft && !ts.has_fft) {
+    std::vector<float> w(2 * N);
+    for (int n = 0; n < 2 * N; ++n) w[n] = (float)std::sin(pi * (n + 0.5) / (2.0 * N));
+    std::vector<float2> pre(N / 2), post(N / 2), w64(64), w256(256);
+    for (int m = 0; m < N / 2; ++m) {
+      pre[m] = make_float2((float)std::cos(pi * (4 * m + 1) / (4.0 * N)), (float)-std::sin(pi * (4 * m + 1) / (4.0 * N)));
+      post[m] = make_float2((float)std::cos(pi * m / (double)N), (float)-std::sin(pi * m / (double)N));
+    }
+    for (int q = 0; q < 64; ++q) w64[q] = make_float2((float)std::cos(2 * pi * q / 64.0), (float)-std::sin(2 * pi * q / 64.0));
+    for (int q = 0; q < 256; ++q) w256[q] = make_float2((float)std::cos(2 * pi * q / 256.0), (float)-std::sin(2 * pi * q / 256.0));
+    MFAC_OK(upload(w, &ts.fft.window));
+    MFAC_OK(upload(pre, &ts.fft.pre));
+    MFAC_OK(upload(post, &ts.fft.post));
+    MFAC_OK(upload(w64, &ts.fft.w64));
+    MFAC_OK(upload(w256, &ts.fft.w256));
+    ts.has_fft = true;
+  }
+  if (!want_fft && !ts.has_dense) {
+    std::vector<float> wc((size_t)2 * N * N), wct((size_t)2 * N * N);
+    for (int n = 0; n < 2 * N; ++n) {
+      const double wn = std::sin(pi * (n + 0.5) / (2.0 * N));
+      for (int k = 0; k < N; ++k) {
+        // exact argument reduction: (2n + N + 1)(2k + 1) mod 8N in integers, then one fp64 cos
+        const long long q = ((long long)(2 * n + N + 1) * (2 * k + 1)) % (8LL * N);
+        const double c = std::cos(pi * (double)q / (4.0 * N));
+        wc[(size_t)n * N + k] = (float)(wn * c);
+        wct[(size_t)k * 2 * N + n] = (float)(2.0 / N * wn * c);
+      }
+    }
+    MFAC_OK(upload(wc, &ts.dense.wc));
+    MFAC_OK(upload(wct, &ts.dense.wct));
+    ts.has_dense = true;
+  }
+  *out = ts;
+  return MFAC_SUCCESS;
+}
+
+// ------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// forward 4-point DFT, natural order in and out
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+  const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = mul_mi(csub(x1, x3));
+  x0 = cadd(t0, t2);
+  x1 = cadd(t1, t3);
+  x2 = csub(t0, t2);
+  x3 = csub(t1, t3);
+}
+// forward 8-point DFT, natural order in and out (radix-2 DIF split, then two 4-point DFTs)
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  const float r = 0.70710678118654752440f;
+  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+  float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+  b1 = make_float2(r * (b1.x + b1.y), r * (b1.y - b1.x));    // * (1 - i)/sqrt2
+  b2 = mul_mi(b2);                                          // * (-i)
+  b3 = make_float2(r * (b3.y - b3.x), -r * (b3.x + b3.y));   // * (-1 - i)/sqrt2
+  dft4(a0, a1, a2, a3);
+  dft4(b0, b1, b2, b3);
+  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+  v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
+// 256-point forward complex FFT of the 8 values each lane holds (element m = lane + 32 j),
+// followed by the DCT-IV post twiddle.  Results are scattered to stage[] (512 floats, aliasing
+// the exchange buffer) as the DCT-IV output: stage[2k] = Re y_k, stage[511-2k] = -Im y_k.
+//   n = 32 n1 + 4 n2 + n3   (lane = 4 n2 + n3, j = n1)      k = k1 + 8 k2 + 64 k3
+__device__ __forceinline__ void fft256_dct4_tail(float2 (&c)[8], float2* scr, const float2* s_post, const float2* s_w64,
+                                                 const float2* s_w256, int lane) {
+  // pass 1: radix-8 over n1, twiddle W64^(n2 k1)
+  dft8(c);
+  {
+    const int n2 = lane >> 2;
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) c[k1] = cmul(c[k1], s_w64[(n2 * k1) & 63]);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) scr[k1 * SCR_STRIDE + lane] = c[k1];
+  }
+  __syncwarp();
+  // pass 2: lane = (k1, n3); radix-8 over n2, twiddle W256^(n3 (k1 + 8 k2))
+  {
+    const int k1 = lane >> 2, n3 = lane & 3;
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) c[n2] = scr[k1 * SCR_STRIDE + 4 * n2 + n3];
+    dft8(c);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) c[k2] = cmul(c[k2], s_w256[(n3 * (k1 + 8 * k2)) & 255]);
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) scr[k1 * SCR_STRIDE + 4 * k2 + n3] = c[k2];
+  }
+  __syncwarp();
+  // pass 3: two (k1,k2) pairs per lane, radix-4 over n3, post twiddle
+  float2 y[8];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int q = lane + 32 * half;
+    const int k1 = q >> 3, k2 = q & 7;
+    const float4* p = reinterpret_cast<const float4*>(scr + k1 * SCR_STRIDE + 4 * k2);
+    const float4 u0 = p[0], u1 = p[1];
+    float2 x0 = make_float2(u0.x, u0.y), x1 = make_float2(u0.z, u0.w), x2 = make_float2(u1.x, u1.y),
+           x3 = make_float2(u1.z, u1.w);
+    dft4(x0, x1, x2, x3);
+    const int k = k1 + 8 * k2;
+    y[4 * half + 0] = cmul(x0, s_post[k]);
+    y[4 * half + 1] = cmul(x1, s_post[k + 64]);
+    y[4 * half + 2] = cmul(x2, s_post[k + 128]);
+    y[4 * half + 3] = cmul(x3, s_post[k + 192]);
+  }
+  __syncwarp();
+  float* stage = reinterpret_cast<float*>(scr);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int q = lane + 32 * half;
+    const int k = (q >> 3) + 8 * (q & 7);
+#pragma unroll
+    for (int k3 = 0; k3 < 4; ++k3) {
+      const int kk = k + 64 * k3;
+      stage[2 * kk] = y[4 * half + k3].x;
+      stage[FFT_N - 1 - 2 * kk] = -y[4 * half + k3].y;
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ forward, N = 512
+// grid (ceil(nf / frames_per_cta), B); 8 warps; dynamic smem:
+//   tables (window 1024 f, pre/post 256 f2 each, w64 64 f2, w256 256 f2) | per-warp exchange | input segment
+__global__ void __launch_bounds__(MDCT_WARPS * 32)
+mdct512_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables tab, StridedIO io, int64_t T, int64_t nf,
+               int hop, int frames_per_cta, int seg_len) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_win = reinterpret_cast<float*>(smem_raw);
+  float2* s_pre = reinterpret_cast<float2*>(s_win + 2 * FFT_N);
+  float2* s_post = s_pre + FFT_H;
+  float2* s_w64 = s_post + FFT_H;
+  float2* s_w256 = s_w64 + 64;
+  float2* s_scr = s_w256 + 256;
+  float* s_seg = reinterpret_cast<float*>(s_scr + MDCT_WARPS * SCR_F2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.y;
+  const int64_t f0 = (int64_t)blockIdx.x * frames_per_cta;
+  const int nframes = (int)min((int64_t)frames_per_cta, nf - f0);
+
+  for (int i = tid; i < 2 * FFT_N; i += blockDim.x) s_win[i] = tab.window[i];
+  for (int i = tid; i < FFT_H; i += blockDim.x) {
+    s_pre[i] = tab.pre[i];
+    s_post[i] = tab.post[i];
+    s_w256[i] = tab.w256[i];
+  }
+  if (tid < 64) s_w64[tid] = tab.w64[tid];
+  // stage the input segment once; frames overlap inside it.  Zero beyond T (implicit padding).
+  {
+    const int64_t s0 = f0 * hop;
+    const int need = (nframes - 1) * hop + 2 * FFT_N;
+    const float* xb = x + b * io.in_clip_stride;
+    for (int i = tid; i < need; i += blockDim.x) {
+      const int64_t s = s0 + i;
+      s_seg[i] = (s < T) ? __ldg(xb + s * io.in_elem_stride) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  float2* scr = s_scr + warp * SCR_F2;
+  for (int f = warp; f < nframes; f += MDCT_WARPS) {
+    const float* z = s_seg + f * hop;
+    float2 c[8];
+    // fold + window + pre-twiddle: c[m] = (u[2m] + i u[N-1-2m]) * pre[m],  h = N/2 = 256
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = lane + 32 * j;
+      float re, im;
+      if (j < 4) {  // m < 128
+        const int a0 = 3 * FFT_H - 1 - 2 * m, a1 = 3 * FFT_H + 2 * m, a2 = FFT_H - 1 - 2 * m, a3 = FFT_H + 2 * m;
+        re = -z[a0] * s_win[a0] - z[a1] * s_win[a1];
+        im = z[a2] * s_win[a2] - z[a3] * s_win[a3];
+      } else {
+        const int a0 = 2 * m - FFT_H, a1 = 3 * FFT_H - 1 - 2 * m, a2 = FFT_H + 2 * m, a3 = 5 * FFT_H - 1 - 2 * m;
+        re = z[a0] * s_win[a0] - z[a1] * s_win[a1];
+        im = -z[a2] * s_win[a2] - z[a3] * s_win[a3];
+      }
+      c[j] = cmul(make_float2(re, im), s_pre[m]);
+    }
+    fft256_dct4_tail(c, scr, s_post, s_w64, s_w256, lane);
+    const float4* st = reinterpret_cast<const float4*>(scr);
+    float* dst = X + b * io.out_clip_stride + (f0 + f) * io.out_elem_stride;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[lane + 32 * i] = st[lane + 32 * i];
+    } else {
+      const float* sf = reinterpret_cast<const float*>(scr);
+      for (int i = lane; i < FFT_N; i += 32) dst[i] = sf[i];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ inverse, N = 512
+// grid (ceil(L / samples_per_cta), B).  Phase 1: DCT-IV of every frame touching the CTA's output range
+// into s_v[frame][N].  Phase 2: each output sample gathers unfold(v_i)[s - i*hop] * w * 2/N over its frames.
+__global__ void __launch_bounds__(MDCT_WARPS * 32)
+imdct512_kernel(const float* __restrict__ X, float* __restrict__ y, FftTables tab, StridedIO io, int64_t nf, int64_t L,
+                int hop, int samples_per_cta, int max_frames) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_win = reinterpret_cast<float*>(smem_raw);
+  float2* s_pre = reinterpret_cast<float2*>(s_win + 2 * FFT_N);
+  float2* s_post = s_pre + FFT_H;
+  float2* s_w64 = s_post + FFT_H;
+  float2* s_w256 = s_w64 + 64;
+  float2* s_scr = s_w256 + 256;
+  float* s_v = reinterpret_cast<float*>(s_scr + MDCT_WARPS * SCR_F2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.y;
+  const int64_t s0 = (int64_t)blockIdx.x * samples_per_cta;
+  const int64_t s1 = min(L, s0 + samples_per_cta);
+  // frames i with i*hop <= s < i*hop + 2N for some s in [s0, s1)
+  int64_t i_lo = (s0 - 2 * FFT_N + 1 + hop - 1);
+  i_lo = i_lo <= 0 ? 0 : i_lo / hop;
+  const int64_t i_hi = min(nf - 1, (s1 - 1) / hop);
+  const int nframes = (int)(i_hi - i_lo + 1);  // <= max_frames by construction
+
+  for (int i = tid; i < 2 * FFT_N; i += blockDim.x) s_win[i] = tab.window[i];
+  for (int i = tid; i < FFT_H; i += blockDim.x) {
+    s_pre[i] = tab.pre[i];
+    s_post[i] = tab.post[i];
+    s_w256[i] = tab.w256[i];
+  }
+  if (tid < 64) s_w64[tid] = tab.w64[tid];
+  __syncthreads();
+
+  float2* scr = s_scr + warp * SCR_F2;
+  for (int f = warp; f < nframes; f += MDCT_WARPS) {
+    const float* src = X + b * io.in_clip_stride + (i_lo + f) * io.in_elem_stride;
+    float* stage = reinterpret_cast<float*>(scr);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(stage)[lane + 32 * i] = __ldg(reinterpret_cast<const float4*>(src) + lane + 32 * i);
+    } else {
+      for (int i = lane; i < FFT_N; i += 32) stage[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    float2 c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = lane + 32 * j;
+      c[j] = cmul(make_float2(stage[2 * m], stage[FFT_N - 1 - 2 * m]), s_pre[m]);
+    }
+    __syncwarp();
+    fft256_dct4_tail(c, scr, s_post, s_w64, s_w256, lane);
+    float4* dst = reinterpret_cast<float4*>(s_v + f * FFT_N);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = reinterpret_cast<const float4*>(scr)[lane + 32 * i];
+    __syncwarp();
+  }
+  __syncthreads();
+
+  const float scale = 2.0f / FFT_N;
+  float* yb = y + b * io.out_clip_stride;
+  for (int64_t s = s0 + tid; s < s1; s += blockDim.x) {
+    int64_t lo = s - 2 * FFT_N + 1 + hop - 1;
+    lo = lo <= 0 ? 0 : lo / hop;
+    const int64_t hi = min(nf - 1, s / hop);
+    float acc = 0.f;
+    for (int64_t i = lo; i <= hi; ++i) {
+      const int n = (int)(s - i * hop);
+      const float* v = s_v + (i - i_lo) * FFT_N;
+      float val;
+      if (n < FFT_H) val = v[FFT_H + n];
+      else if (n < 3 * FFT_H) val = -v[3 * FFT_H - 1 - n];
+      else val = -v[n - 3 * FFT_H];
+      acc = fmaf(val, s_win[n], acc);
+    }
+    yb[s * io.out_elem_stride] = acc * scale;
+  }
+}
+
+// ------------------------------------------------------------------ generic N: dense contraction
+constexpr int DENSE_FR = 4;       // frames per CTA
+constexpr int DENSE_THREADS = 128;
+
+__global__ void __launch_bounds__(DENSE_THREADS)
+mdct_dense_kernel(const float* __restrict__ x, float* __restrict__ X, const float* __restrict__ wc, StridedIO io, int64_t T,
+                  int64_t nf, int N, int hop) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_x = reinterpret_cast<float*>(smem_raw);  // [DENSE_FR][2N]
+  const int64_t b = blockIdx.z;
+  const int64_t f0 = (int64_t)blockIdx.y * DENSE_FR;
+  const int nframes = (int)min((int64_t)DENSE_FR, nf - f0);
+  const float* xb = x + b * io.in_clip_stride;
+  for (int i = threadIdx.x; i < DENSE_FR * 2 * N; i += blockDim.x) {
+    const int f = i / (2 * N), n = i % (2 * N);
+    const int64_t s = (f0 + f) * hop + n;
+    s_x[i] = (f < nframes && s < T) ? __ldg(xb + s * io.in_elem_stride) : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * DENSE_THREADS + threadIdx.x;
+  if (k >= N) return;
+  float acc[DENSE_FR];
+#pragma unroll
+  for (int f = 0; f < DENSE_FR; ++f) acc[f] = 0.f;
+  for (int n = 0; n < 2 * N; ++n) {
+    const float c = __ldg(wc + (int64_t)n * N + k);
+#pragma unroll
+    for (int f = 0; f < DENSE_FR; ++f) acc[f] = fmaf(s_x[f * 2 * N + n], c, acc[f]);
+  }
+  for (int f = 0; f < nframes; ++f) X[b * io.out_clip_stride + (f0 + f) * io.out_elem_stride + k] = acc[f];
+}
+
+__global__ void __launch_bounds__(256)
+imdct_dense_kernel(const float* __restrict__ X, float* __restrict__ y, const float* __restrict__ wct, StridedIO io,
+                   int64_t nf, int64_t L, int N, int hop) {
+  const int64_t b = blockIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= L) return;
+  int64_t lo = s - 2 * N + 1 + hop - 1;
+  lo = lo <= 0 ? 0 : lo / hop;
+  const int64_t hi = min(nf - 1, s / hop);
+  float acc = 0.f;
+  for (int64_t i = lo; i <= hi; ++i) {
+    const int n = (int)(s - i * hop);
+    const float* Xi = X + b * io.in_clip_stride + i * io.in_elem_stride;
+    float a = 0.f;
+    for (int k = 0; k < N; ++k) a = fmaf(__ldg(Xi + k), __ldg(wct + (int64_t)k * 2 * N + n), a);
+    acc += a;
+  }
+  y[b * io.out_clip_stride + s * io.out_elem_stride] = acc;
+}
+
+constexpr int TABLE_BYTES = 2 * FFT_N * 4 + (FFT_H * 2 + 64 + 256) * 8;
+constexpr int SCRATCH_BYTES = MDCT_WARPS * SCR_F2 * 8;
+
+}  // namespace
+
+int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, int N, int hop, cudaStream_t stream) {
+  if (!x || !X) return MFAC_ERR_NULL;
+  if (B <= 0 || T <= 0 || N <= 0 || hop <= 0) return MFAC_ERR_BAD_SHAPE;
+  if (B > 65535) return MFAC_ERR_UNSUPPORTED;
+  const int64_t nf = T < N ? 1 : (T - N) / hop + 1;
+  TableSet ts;
+  // frames per CTA: as many as fit a ~48 KB input segment, at most 32
+  int fpc = (int)((12288 - 2 * FFT_N) / hop + 1);
+  fpc = fpc < 1 ? 1 : (fpc > 32 ? 32 : fpc);
+  if (nf < fpc) fpc = (int)nf;
+  const int64_t seg_len = (int64_t)(fpc - 1) * hop + 2 * FFT_N;
+  if (N == FFT_N && seg_len <= 40960) {
+    MFAC_OK(get_tables(N, true, &ts));
+    const size_t smem = TABLE_BYTES + SCRATCH_BYTES + (size_t)seg_len * 4;
+    static bool configured = false;
+    if (!configured) {
+      MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(nf, fpc), (unsigned)B);
+    mdct512_kernel<<<grid, MDCT_WARPS * 32, smem, stream>>>(x, X, ts.fft, io, T, nf, hop, fpc, (int)seg_len);
+    count_launch();
+    return launch_status();
+  }
+  if (N > 4096) return MFAC_ERR_UNSUPPORTED;
+  MFAC_OK(get_tables(N, false, &ts));
+  const size_t smem = (size_t)DENSE_FR * 2 * N * 4;
+  static bool configured_dense = false;
+  if (!configured_dense) {
+    MFAC_CUDA_OK(cudaFuncSetAttribute(mdct_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dense = true;
+  }
+  const int64_t fy = ceil_div<int64_t>(nf, DENSE_FR);
+  if (fy > 65535) return MFAC_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(N, DENSE_THREADS), (unsigned)fy, (unsigned)B);
+  mdct_dense_kernel<<<grid, DENSE_THREADS, smem, stream>>>(x, X, ts.dense.wc, io, T, nf, N, hop);
+  count_launch();
+  return launch_status();
+}
+
+int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, int N, int hop, cudaStream_t stream) {
+  if (!X || !y) return MFAC_ERR_NULL;
+  if (B <= 0 || nf <= 0 || N <= 0 || hop <= 0) return MFAC_ERR_BAD_SHAPE;
+  if (B > 65535) return MFAC_ERR_UNSUPPORTED;
+  const int64_t L = (nf - 1) * hop + 2 * (int64_t)N;
+  TableSet ts;
+  // output samples per CTA: 32 hops (bounded), frames touching them: spc/hop + 2N/hop + 2
+  int64_t spc = 32LL * hop;
+  if (spc > 16384) spc = 16384;
+  if (spc < 1024) spc = 1024;
+  const int max_frames = (int)((spc - 1) / hop + (2 * FFT_N - 1) / hop + 2);
+  const size_t smem = TABLE_BYTES + SCRATCH_BYTES + (size_t)max_frames * FFT_N * 4;
+  if (N == FFT_N && smem <= 160 * 1024) {  // tiny hops (< ~16) fall through to the dense path
+    MFAC_OK(get_tables(N, true, &ts));
+    static bool configured = false;
+    if (!configured) {
+      MFAC_CUDA_OK(cudaFuncSetAttribute(imdct512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(L, spc), (unsigned)B);
+    imdct512_kernel<<<grid, MDCT_WARPS * 32, smem, stream>>>(X, y, ts.fft, io, nf, L, hop, (int)spc, max_frames);
+    count_launch();
+    return launch_status();
+  }
+  if (N > 4096) return MFAC_ERR_UNSUPPORTED;
+  MFAC_OK(get_tables(N, false, &ts));
+  dim3 grid((unsigned)ceil_div<int64_t>(L, 256), (unsigned)B);
+  imdct_dense_kernel<<<grid, 256, 0, stream>>>(X, y, ts.dense.wct, io, nf, L, N, hop);
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace mfac
+
+// ------------------------------------------------------------------ C ABI
+using mfac::StridedIO;
+
+extern "C" {
+
+int64_t mfac_mdct_num_frames(int64_t T, int32_t N, int32_t hop) {
+  if (T <= 0 || N <= 0 || hop <= 0) return MFAC_ERR_BAD_SHAPE;
+  return T < N ? 1 : (T - N) / hop + 1;
+}
+int64_t mfac_imdct_length(int64_t nf, int32_t N, int32_t hop) {
+  if (nf <= 0 || N <= 0 || hop <= 0) return MFAC_ERR_BAD_SHAPE;
+  return (nf - 1) * hop + 2 * (int64_t)N;
+}
+
+int mfac_mdct_strided_f32(const float* x, int64_t x_clip_stride, int64_t x_elem_stride, float* X, int64_t X_clip_stride,
+                          int64_t X_frame_stride, int64_t B, int64_t T, int32_t N, int32_t hop, void* stream) {
+  StridedIO io{x_clip_stride, x_elem_stride, X_clip_stride, X_frame_stride};
+  return mfac::mdct_forward(x, X, io, B, T, N, hop, (cudaStream_t)stream);
+}
+int mfac_imdct_strided_f32(const float* X, int64_t X_clip_stride, int64_t X_frame_stride, float* y, int64_t y_clip_stride,
+                           int64_t y_elem_stride, int64_t B, int64_t nf, int32_t N, int32_t hop, void* stream) {
+  StridedIO io{X_clip_stride, X_frame_stride, y_clip_stride, y_elem_stride};
+  return mfac::mdct_inverse(X, y, io, B, nf, N, hop, (cudaStream_t)stream);
+}
+int mfac_mdct_f32(const float* x, float* X, int64_t B, int64_t T, int32_t N, int32_t hop, void* stream) {
+  const int64_t nf = mfac_mdct_num_frames(T, N, hop);
+  if (nf < 0) return (int)nf;
+  return mfac_mdct_strided_f32(x, T, 1, X, nf * N, N, B, T, N, hop, stream);
+}
+int mfac_imdct_f32(const float* X, float* y, int64_t B, int64_t nf, int32_t N, int32_t hop, void* stream) {
+  const int64_t L = mfac_imdct_length(nf, N, hop);
+  if (L < 0) return (int)L;
+  return mfac_imdct_strided_f32(X, nf * N, N, y, L, 1, B, nf, N, hop, stream);
+}
+
+}  // extern "C"

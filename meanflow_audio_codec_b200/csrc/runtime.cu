@@ -1,0 +1,106 @@
+// Process-wide runtime helpers of libmfac: device properties, TMA tensor-map encoding
+// (driver entry point resolved at run time so the library links against cudart only),
+// launch counters and the GEMM test hook.
+#include <atomic>
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace mfac {
+
+namespace {
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_simt{0};
+std::atomic<int> g_num_sms{0};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void resolve_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess) {
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+}
+}  // namespace
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool simt_gemm_enabled() { return g_simt.load(std::memory_order_relaxed) != 0; }
+
+int num_sms() {
+  int n = g_num_sms.load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  g_num_sms.store(n, std::memory_order_relaxed);
+  return n;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                   int box_outer) {
+  std::call_once(g_encode_once, resolve_encode);
+  if (!g_encode) return MFAC_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return MFAC_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFAC_SUCCESS : MFAC_ERR_DRIVER;
+}
+
+}  // namespace mfac
+
+extern "C" {
+
+int mfac_version(void) { return 100; }
+
+const char* mfac_status_string(int status) {
+  switch (status) {
+    case MFAC_SUCCESS: return "success";
+    case MFAC_ERR_BAD_SHAPE: return "bad shape";
+    case MFAC_ERR_UNSUPPORTED: return "unsupported configuration";
+    case MFAC_ERR_WORKSPACE: return "workspace missing or too small";
+    case MFAC_ERR_NULL: return "null pointer";
+    case MFAC_ERR_DRIVER: return "CUDA driver entry point unavailable";
+    case MFAC_ERR_NCCL: return "NCCL unavailable or failed";
+    default: break;
+  }
+  if (status <= -1000) return cudaGetErrorString((cudaError_t)(-status - 1000));
+  return "unknown status";
+}
+
+int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int64_t M, int64_t N, int64_t K, int32_t a_mn_major,
+                         int32_t b_mn_major, int32_t block_n, void* stream) {
+  using namespace mfac;
+  if (!A || !B || !Cout) return MFAC_ERR_NULL;
+  GemmOperandDesc a{A, a_mn_major ? M : K, a_mn_major != 0};
+  GemmOperandDesc b{B, b_mn_major ? N : K, b_mn_major != 0};
+  EpiStoreF32 epi{Cout, N};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(a, b, (int)M, (int)N, (int)K, epi, s, block_n);
+  if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(a, b, (int)M, (int)N, (int)K, epi, s, block_n);
+  if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(a, b, (int)M, (int)N, (int)K, epi, s, block_n);
+  return launch_gemm<true, true>(a, b, (int)M, (int)N, (int)K, epi, s, block_n);
+}
+
+int mfac_debug_set_simt_gemm(int32_t on) {
+  mfac::g_simt.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+int mfac_debug_counters(int64_t* kernel_launches) {
+  if (kernel_launches) *kernel_launches = mfac::g_launches.load();
+  return MFAC_SUCCESS;
+}
+
+}  // extern "C"
