@@ -6,3 +6,9 @@ C ABI (``include/mfac.h``, ``libmfac.so``).  See DESIGN.md.
 """
 from ._lib import LIB_PATH, MfacError  # noqa: F401
 from .mdct import MDCTConfig, MDCTLayer, IMDCTLayer, imdct, mdct  # noqa: F401
+from .tokenization import (MDCTTokenization, compute_token_shape, compute_tokenized_dimension,  # noqa: F401
+                           create_tokenization_strategy)
+from .mlp_flow import AdamW, ConditionalFlow, TrainState, adamw  # noqa: F401
+from .loss_strategies import (ImprovedMeanFlowLoss, LinearNoiseSchedule, LossStrategy,  # noqa: F401
+                              MeanFlowTimeSampling, train_step)
+from .sampling import sample, sample_mean_flow  # noqa: F401

@@ -1,0 +1,454 @@
+// Orchestration of the MLP velocity network, the iMF loss/gradient step and the samplers.
+//
+// ref (paths inside /root/reference/meanflow_audio_codec/):
+//   ConditionalFlow.__call__ / encode     models/mlp_flow.py:125-230
+//   ImprovedMeanFlowLoss.compute_loss     trainers/loss_strategies.py:227-280
+//   sample (Heun, h = 0)                  evaluators/sampling.py:5-95
+//
+// Every matrix product is a launch of the tcgen05 GEMM in gemm.cuh with a fused epilogue from
+// imf_kernels.cuh; the remaining work is the row kernels there.  The three network evaluations
+// of the iMF loss run as:  v-pass (B rows)  ->  u-pass primal (saves activations) interleaved with
+// the tangent pass block by block (the JVP shares W1c/W2c/W1/W2 with the primal)  ->  loss  ->
+// backward through the primal u rows and the encoder only (v and du/dt carry no gradient).
+#include "gemm.cuh"
+#include "imf_kernels.cuh"
+
+namespace mfac {
+
+namespace {
+
+struct Shadow {
+  const __nv_bfloat16* w;
+  const float* b;
+  Shadow(const void* p, const Dims& d)
+      : w(reinterpret_cast<const __nv_bfloat16*>(p)),
+        b(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p) + d.bias_section_bytes_offset)) {}
+};
+
+inline unsigned blocks_for(int64_t n, int t) { return (unsigned)ceil_div<int64_t>(n, t); }
+
+// ---- GEMM flavours ---------------------------------------------------------------------
+// y[M,N] = A[M,K] @ W[K,N]           A K-major (ld lda), W = shadow kernel [in=K, out=N] (MN-major B)
+template <class Epi>
+int gemm_fwd(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+  return launch_gemm<false, true>(GemmOperandDesc{A, lda, false}, GemmOperandDesc{W, N, true}, M, N, K, epi, s);
+}
+// y[M,N] = G[M,K] @ W^T              W = shadow kernel [in=N, out=K] read as K-major B
+template <class Epi>
+int gemm_dx(const __nv_bfloat16* G, int ldg, const __nv_bfloat16* W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+  return launch_gemm<false, false>(GemmOperandDesc{G, ldg, false}, GemmOperandDesc{W, K, false}, M, N, K, epi, s);
+}
+// dW[M,N] = Act[Bk,M]^T @ G[Bk,N]    both operands MN-major (batch is the contraction)
+template <class Epi>
+int gemm_dw(const __nv_bfloat16* Act, int lda, const __nv_bfloat16* G, int ldg, int M, int N, int Bk, const Epi& epi,
+            cudaStream_t s) {
+  return launch_gemm<true, true>(GemmOperandDesc{Act, lda, true}, GemmOperandDesc{G, ldg, true}, M, N, Bk, epi, s);
+}
+
+int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
+  const size_t smem = (size_t)d.Ip * 4 * (tangent ? 2 : 1);
+  if (smem > 200 * 1024) return MFAC_ERR_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    MFAC_CUDA_OK(cudaFuncSetAttribute(lnmod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(lnmod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(imf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (tangent) lnmod_kernel<true><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
+  else lnmod_kernel<false><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
+  count_launch();
+  return launch_status();
+}
+
+// Scratch of one (unsaved) forward evaluation.
+struct FwdScratch {
+  __nv_bfloat16 *gc, *m, *hin, *g;
+  void plan(Arena& ar, const Dims& d, int64_t B) {
+    gc = ar.take<__nv_bfloat16>(B * d.Cp);
+    m = ar.take<__nv_bfloat16>(B * d.Mp);
+    hin = ar.take<__nv_bfloat16>(B * d.Ip);
+    g = ar.take<__nv_bfloat16>(B * d.Ip);
+  }
+};
+
+// x <- f(x, cond, lat) in place over all blocks (no activations kept).
+int forward_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* cond, const float* lat, float* x, int64_t B,
+                 const FwdScratch& sc, cudaStream_t s) {
+  const int M = (int)B;
+  const float inv_nb = 1.0f / (float)d.nb;
+  for (int k = 0; k < d.nb; ++k) {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    const float* bias = sh.b + k * d.b_blk_stride;
+    MFAC_OK(gemm_fwd(cond, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiBiasGelu{bias + d.b_c1, sc.gc, nullptr, d.Cp}, s));
+    MFAC_OK(gemm_fwd(sc.gc, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, EpiLinearBf16{bias + d.b_c2, sc.m, d.Mp}, s));
+    LnModArgs la{lat, x, sc.m, sc.hin, nullptr, nullptr, nullptr, nullptr, nullptr};
+    MFAC_OK(lnmod(false, la, d, B, s));
+    MFAC_OK(gemm_fwd(sc.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiBiasGelu{bias + d.b_m1, sc.g, nullptr, d.Ip}, s));
+    MFAC_OK(gemm_fwd(sc.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
+                     EpiBlockOut{bias + d.b_m2, sc.m, x, x, nullptr, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
+  }
+  return MFAC_SUCCESS;
+}
+
+// latents = enc2(gelu(enc1(x)));  keeps a_e / g_e when asked (backward)
+int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_bfloat16* a_e, __nv_bfloat16* g_e, float* lat,
+                 int64_t B, cudaStream_t s) {
+  MFAC_OK(gemm_fwd(xb, d.Dp, sh.w + d.s_e1w, (int)B, d.Hep, d.Dp, EpiBiasGelu{sh.b + d.b_e1, g_e, a_e, d.Hep}, s));
+  MFAC_OK(gemm_fwd(g_e, d.Hep, sh.w + d.s_e2w, (int)B, d.Lp, d.Hep, EpiLinearF32{sh.b + d.b_e2, lat, d.Lp}, s));
+  return MFAC_SUCCESS;
+}
+
+int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* partial, float* out, int kind, int limit, const Dims& d,
+           cudaStream_t s) {
+  const int R = (int)ceil_div<int64_t>(B, COLSUM_ROWS);
+  colsum_partial_kernel<<<dim3(ld / 64, R), 256, 0, s>>>(G, ld, B, partial);
+  count_launch();
+  colsum_final_kernel<<<blocks_for(ld, 128), 128, 0, s>>>(partial, ld, R, out, kind, limit, d);
+  count_launch();
+  return launch_status();
+}
+
+// ---- workspaces ------------------------------------------------------------------------
+struct SavedBlock {
+  __nv_bfloat16 *ac, *gc, *m, *hin, *a, *g, *o;
+  float *mu, *rstd;
+};
+
+struct LossGradPlan {
+  // prologue
+  float *e, *z, *t, *r;
+  __nv_bfloat16 *xb, *cond_v, *cond_u, *dcond_u;
+  // encoder
+  __nv_bfloat16 *a_e, *g_e;
+  float* lat;
+  // v pass
+  float* v;
+  FwdScratch fs;
+  // u pass
+  float* xs;  // [(nb+1), B, Dp]
+  SavedBlock blk[64];
+  // tangent transients
+  __nv_bfloat16 *gcd, *md, *hind, *gd;
+  float* xd;
+  // loss / backward
+  float *row_loss, *g_x, *g_lat, *g_hin, *partial;
+  __nv_bfloat16 *g_o, *g_a, *g_m, *g_ac, *g_latb, *g_ae;
+
+  void plan(Arena& ar, const Dims& d, int64_t B) {
+    e = ar.take<float>(B * d.Dp);
+    z = ar.take<float>(B * d.Dp);
+    t = ar.take<float>(B);
+    r = ar.take<float>(B);
+    xb = ar.take<__nv_bfloat16>(B * d.Dp);
+    cond_v = ar.take<__nv_bfloat16>(B * d.Cp);
+    cond_u = ar.take<__nv_bfloat16>(B * d.Cp);
+    dcond_u = ar.take<__nv_bfloat16>(B * d.Cp);
+    a_e = ar.take<__nv_bfloat16>(B * d.Hep);
+    g_e = ar.take<__nv_bfloat16>(B * d.Hep);
+    lat = ar.take<float>(B * d.Lp);
+    v = ar.take<float>(B * d.Dp);
+    fs.plan(ar, d, B);
+    xs = ar.take<float>((int64_t)(d.nb + 1) * B * d.Dp);
+    for (int k = 0; k < d.nb; ++k) {
+      SavedBlock& sb = blk[k];
+      sb.ac = ar.take<__nv_bfloat16>(B * d.Cp);
+      sb.gc = ar.take<__nv_bfloat16>(B * d.Cp);
+      sb.m = ar.take<__nv_bfloat16>(B * d.Mp);
+      sb.hin = ar.take<__nv_bfloat16>(B * d.Ip);
+      sb.a = ar.take<__nv_bfloat16>(B * d.Ip);
+      sb.g = ar.take<__nv_bfloat16>(B * d.Ip);
+      sb.o = ar.take<__nv_bfloat16>(B * d.Dp);
+      sb.mu = ar.take<float>(B);
+      sb.rstd = ar.take<float>(B);
+    }
+    gcd = ar.take<__nv_bfloat16>(B * d.Cp);
+    md = ar.take<__nv_bfloat16>(B * d.Mp);
+    hind = ar.take<__nv_bfloat16>(B * d.Ip);
+    gd = ar.take<__nv_bfloat16>(B * d.Ip);
+    xd = ar.take<float>(B * d.Dp);
+    row_loss = ar.take<float>(B);
+    g_x = ar.take<float>(B * d.Dp);
+    g_lat = ar.take<float>(B * d.Lp);
+    g_hin = ar.take<float>(B * d.Ip);
+    partial = ar.take<float>(ceil_div<int64_t>(B, COLSUM_ROWS) * d.Mp);
+    g_o = ar.take<__nv_bfloat16>(B * d.Dp);
+    g_a = ar.take<__nv_bfloat16>(B * d.Ip);
+    g_m = ar.take<__nv_bfloat16>(B * d.Mp);
+    g_ac = ar.take<__nv_bfloat16>(B * d.Cp);
+    g_latb = ar.take<__nv_bfloat16>(B * d.Lp);
+    g_ae = ar.take<__nv_bfloat16>(B * d.Hep);
+  }
+};
+
+struct ForwardPlan {
+  float *x, *lat;
+  __nv_bfloat16 *xb, *cond, *a_e, *g_e;
+  FwdScratch fs;
+  void plan(Arena& ar, const Dims& d, int64_t B) {
+    x = ar.take<float>(B * d.Dp);
+    lat = ar.take<float>(B * d.Lp);
+    xb = ar.take<__nv_bfloat16>(B * d.Dp);
+    cond = ar.take<__nv_bfloat16>(B * d.Cp);
+    a_e = nullptr;
+    g_e = ar.take<__nv_bfloat16>(B * d.Hep);
+    fs.plan(ar, d, B);
+  }
+};
+
+struct SamplePlan {
+  float *x, *x2, *k1, *k2, *tmp, *lat;
+  __nv_bfloat16* cond;
+  FwdScratch fs;
+  void plan(Arena& ar, const Dims& d, int64_t B) {
+    x = ar.take<float>(B * d.Dp);
+    x2 = ar.take<float>(B * d.Dp);
+    k1 = ar.take<float>(B * d.Dp);
+    k2 = ar.take<float>(B * d.Dp);
+    tmp = ar.take<float>(B * d.Dp);
+    lat = ar.take<float>(B * d.Lp);
+    cond = ar.take<__nv_bfloat16>(B * d.Cp);
+    fs.plan(ar, d, B);
+  }
+};
+
+}  // namespace
+}  // namespace mfac
+
+using namespace mfac;
+
+extern "C" {
+
+size_t mfac_workspace_bytes(int32_t kind, const MfacMlpDims* dims, int64_t B) {
+  Dims d;
+  if (make_dims(dims, &d) != MFAC_SUCCESS || B <= 0 || d.nb > 64) return 0;
+  Arena ar(nullptr, 0);
+  if (kind == MFAC_WS_FORWARD) { ForwardPlan p; p.plan(ar, d, B); }
+  else if (kind == MFAC_WS_LOSS_GRAD) { LossGradPlan p; p.plan(ar, d, B); }
+  else if (kind == MFAC_WS_SAMPLE) { SamplePlan p; p.plan(ar, d, B); }
+  else return 0;
+  return ar.off + 256;
+}
+
+int mfac_mlp_encode(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x, float* latents,
+                    int64_t B, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  Dims d;
+  MFAC_OK(make_dims(dims, &d));
+  if (!shadow || !x || !latents) return MFAC_ERR_NULL;
+  if (B <= 0 || B > 0x7fffffff) return MFAC_ERR_BAD_SHAPE;
+  if (!ws) return MFAC_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  ForwardPlan p;
+  p.plan(ar, d, B);
+  if (ar.overflow) return MFAC_ERR_WORKSPACE;
+  Shadow sh(shadow, d);
+  pad_rows_kernel<<<blocks_for(B * d.Dp, 256), 256, 0, s>>>(x, d.D, nullptr, p.xb, d.Dp, B);
+  count_launch();
+  MFAC_OK(encoder_pass(d, sh, p.xb, nullptr, p.g_e, p.lat, B, s));
+  unpad_rows_kernel<<<blocks_for(B * d.L, 256), 256, 0, s>>>(p.lat, d.Lp, latents, d.L, B);
+  count_launch();
+  return launch_status();
+}
+
+int mfac_mlp_forward(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x, const float* time,
+                     const float* latents, float* out, int64_t B, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  Dims d;
+  MFAC_OK(make_dims(dims, &d));
+  if (!shadow || !x || !time || !out) return MFAC_ERR_NULL;
+  if (B <= 0 || B > 0x7fffffff || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if (!ws) return MFAC_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  ForwardPlan p;
+  p.plan(ar, d, B);
+  if (ar.overflow) return MFAC_ERR_WORKSPACE;
+  Shadow sh(shadow, d);
+  pad_rows_kernel<<<blocks_for(B * d.Dp, 256), 256, 0, s>>>(x, d.D, p.x, nullptr, d.Dp, B);
+  count_launch();
+  if (latents) {
+    pad_rows_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(latents, d.L, p.lat, nullptr, d.Lp, B);
+    count_launch();
+  }
+  cond_from_time_kernel<<<(unsigned)B, 128, 0, s>>>(time, p.cond, d);
+  count_launch();
+  MFAC_OK(forward_pass(d, sh, p.cond, latents ? p.lat : nullptr, p.x, B, p.fs, s));
+  unpad_rows_kernel<<<blocks_for(B * d.D, 256), 256, 0, s>>>(p.x, d.Dp, out, d.D, B);
+  count_launch();
+  return launch_status();
+}
+
+int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
+                       const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
+                       const MfacImfAux* aux, int64_t B, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  Dims d;
+  MFAC_OK(make_dims(dims, &d));
+  if (!cfg || !shadow || !x || !loss || !grads) return MFAC_ERR_NULL;
+  if (B <= 0 || B > 0x7fffffff || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if ((t == nullptr) != (r == nullptr)) return MFAC_ERR_NULL;
+  if (!ws) return MFAC_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  LossGradPlan p;
+  p.plan(ar, d, B);
+  if (ar.overflow) return MFAC_ERR_WORKSPACE;
+  Shadow sh(shadow, d);
+  const int M = (int)B;
+  const float inv_nb = 1.0f / (float)d.nb;
+  const size_t row_bytes = (size_t)B * d.Dp * 4;
+
+  // ---- prologue: (e, t, r), z_t, cond rows
+  PrepArgs pa{x, e, t, r, p.e, p.z, p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};
+  imf_prep_kernel<<<(unsigned)B, ROW_THREADS, 0, s>>>(pa, d);
+  count_launch();
+  // ---- latents = encode(x)
+  MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
+  // ---- v = f(z, [t, 0], lat)
+  MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.z, row_bytes, cudaMemcpyDeviceToDevice, s));
+  MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
+  // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
+  MFAC_CUDA_OK(cudaMemcpyAsync(p.xs, p.z, row_bytes, cudaMemcpyDeviceToDevice, s));
+  for (int k = 0; k < d.nb; ++k) {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    const float* bias = sh.b + k * d.b_blk_stride;
+    SavedBlock& sb = p.blk[k];
+    float* x_in = p.xs + (int64_t)k * B * d.Dp;
+    float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp;
+    const float* xd_in = k == 0 ? p.v : p.xd;
+    // modulation, primal and tangent
+    MFAC_OK(gemm_fwd(p.cond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiBiasGelu{bias + d.b_c1, sb.gc, sb.ac, d.Cp}, s));
+    MFAC_OK(gemm_fwd(sb.gc, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, EpiLinearBf16{bias + d.b_c2, sb.m, d.Mp}, s));
+    MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiMulDgelu{sb.ac, p.gcd, d.Cp}, s));
+    MFAC_OK(gemm_fwd(p.gcd, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, EpiLinearBf16{nullptr, p.md, d.Mp}, s));
+    LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd};
+    MFAC_OK(lnmod(true, la, d, B, s));
+    MFAC_OK(gemm_fwd(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiBiasGelu{bias + d.b_m1, sb.g, sb.a, d.Ip}, s));
+    MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
+    MFAC_OK(gemm_fwd(sb.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
+                     EpiBlockOut{bias + d.b_m2, sb.m, x_in, x_out, sb.o, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
+    MFAC_OK(gemm_fwd(p.gd, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
+                     EpiBlockOutTangent{sb.m, p.md, sb.o, xd_in, p.xd, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
+  }
+  const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
+  // ---- loss and its seed gradient
+  LossArgs lo{u, p.xd, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};
+  imf_loss_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Dp * 4, s>>>(lo, d);
+  count_launch();
+  sum_rows_kernel<<<1, 1024, 0, s>>>(p.row_loss, B, loss);
+  count_launch();
+  // ---- backward through the primal u rows
+  MFAC_CUDA_OK(cudaMemsetAsync(p.g_lat, 0, (size_t)B * d.Lp * 4, s));
+  for (int k = d.nb - 1; k >= 0; --k) {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    SavedBlock& sb = p.blk[k];
+    float* gk = grads + (int64_t)k * d.blk_stride;
+    const float* x_in = p.xs + (int64_t)k * B * d.Dp;
+    bwd_block_out_kernel<<<blocks_for(B * d.Dp, 256), 256, 0, s>>>(p.g_x, sb.m, sb.o, p.g_o, p.g_m, d, B);
+    count_launch();
+    MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, d}, s));
+    MFAC_OK(colsum(p.g_o, d.Dp, B, p.partial, gk + d.o_m2b, MAP_ID, d.D, d, s));
+    MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
+    MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, d}, s));
+    MFAC_OK(colsum(p.g_a, d.Ip, B, p.partial, gk + d.o_m1b, MAP_CM, 0, d, s));
+    MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearF32{nullptr, p.g_hin, d.Ip}, s));
+    LnBwdArgs lb{p.g_hin, p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
+    ln_bwd_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Ip * 8, s>>>(lb, d);
+    count_launch();
+    MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
+                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, d}, s));
+    MFAC_OK(colsum(p.g_m, d.Mp, B, p.partial, gk + d.o_c2b, MAP_MM, 0, d, s));
+    MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
+    MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, d}, s));
+    MFAC_OK(colsum(p.g_ac, d.Cp, B, p.partial, gk + d.o_c1b, MAP_ID, d.C, d, s));
+  }
+  // ---- encoder backward
+  f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);
+  count_launch();
+  MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, d}, s));
+  MFAC_OK(colsum(p.g_latb, d.Lp, B, p.partial, grads + d.o_e2b, MAP_ID, d.L, d, s));
+  MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, s));
+  MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, d}, s));
+  MFAC_OK(colsum(p.g_ae, d.Hep, B, p.partial, grads + d.o_e1b, MAP_ID, d.He, d, s));
+  // ---- optional intermediates for parity tests
+  if (aux) {
+    const unsigned nbk = blocks_for(B * d.D, 256);
+    if (aux->v) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.v, d.Dp, aux->v, d.D, B); count_launch(); }
+    if (aux->u) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(u, d.Dp, aux->u, d.D, B); count_launch(); }
+    if (aux->dudt) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.xd, d.Dp, aux->dudt, d.D, B); count_launch(); }
+    if (aux->e) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.e, d.Dp, aux->e, d.D, B); count_launch(); }
+    if (aux->t) MFAC_CUDA_OK(cudaMemcpyAsync(aux->t, p.t, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    if (aux->r) MFAC_CUDA_OK(cudaMemcpyAsync(aux->r, p.r, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return launch_status();
+}
+
+int mfac_sample(const MfacMlpDims* dims, const float* params, const void* shadow, const float* latents, const float* noise,
+                int32_t mode, int32_t n_steps, float guidance_scale, uint64_t seed, float* out, int64_t B, void* ws,
+                size_t ws_bytes, void* stream) {
+  (void)params;
+  Dims d;
+  MFAC_OK(make_dims(dims, &d));
+  if (!shadow || !latents || !out) return MFAC_ERR_NULL;
+  if (B <= 0 || B > 0x7fffffff || n_steps <= 0 || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if (mode != MFAC_SAMPLE_HEUN && mode != MFAC_SAMPLE_MF) return MFAC_ERR_UNSUPPORTED;
+  if (!ws) return MFAC_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  SamplePlan p;
+  p.plan(ar, d, B);
+  if (ar.overflow) return MFAC_ERR_WORKSPACE;
+  Shadow sh(shadow, d);
+  const int64_t n = B * d.Dp;
+  const size_t row_bytes = (size_t)n * 4;
+  const unsigned nblk = blocks_for(n, 256);
+  pad_rows_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(latents, d.L, p.lat, nullptr, d.Lp, B);
+  count_launch();
+  if (noise) pad_rows_kernel<<<nblk, 256, 0, s>>>(noise, d.D, p.x, nullptr, d.Dp, B);
+  else fill_normal_kernel<<<blocks_for(n / 4, 256), 256, 0, s>>>(p.x, d.Dp, d.D, B, seed);
+  count_launch();
+
+  // dst = f(src, [t, h]) with optional classifier-free guidance (sampling.py:62-81)
+  auto eval_f = [&](const float* src, float t, float h, float* dst) -> int {
+    cond_const_kernel<<<(unsigned)B, 128, 0, s>>>(t, h, p.cond, d);
+    count_launch();
+    MFAC_CUDA_OK(cudaMemcpyAsync(dst, src, row_bytes, cudaMemcpyDeviceToDevice, s));
+    MFAC_OK(forward_pass(d, sh, p.cond, p.lat, dst, B, p.fs, s));
+    if (guidance_scale != 1.0f) {
+      MFAC_CUDA_OK(cudaMemcpyAsync(p.tmp, src, row_bytes, cudaMemcpyDeviceToDevice, s));
+      MFAC_OK(forward_pass(d, sh, p.cond, nullptr, p.tmp, B, p.fs, s));
+      axpy2_kernel<<<nblk, 256, 0, s>>>(nullptr, 1.0f, guidance_scale, dst, 1.0f - guidance_scale, p.tmp, dst, n);
+      count_launch();
+    }
+    return MFAC_SUCCESS;
+  };
+
+  if (mode == MFAC_SAMPLE_HEUN) {
+    const float dt = 1.0f / (float)n_steps;
+    for (int i = 0; i < n_steps; ++i) {
+      // jnp.linspace(1, 0, n)[i]; n = 1 gives [1.0]
+      const float t = n_steps == 1 ? 1.0f : 1.0f - (float)i / (float)(n_steps - 1);
+      MFAC_OK(eval_f(p.x, t, 0.f, p.k1));
+      axpy2_kernel<<<nblk, 256, 0, s>>>(p.x, -dt, 1.0f, p.k1, 0.f, nullptr, p.x2, n);
+      count_launch();
+      MFAC_OK(eval_f(p.x2, t - dt, 0.f, p.k2));
+      axpy2_kernel<<<nblk, 256, 0, s>>>(p.x, -0.5f * dt, 1.0f, p.k1, 1.0f, p.k2, p.x, n);
+      count_launch();
+    }
+  } else {
+    for (int i = 0; i < n_steps; ++i) {
+      const float t = 1.0f - (float)i / (float)n_steps, r = 1.0f - (float)(i + 1) / (float)n_steps;
+      MFAC_OK(eval_f(p.x, t, t - r, p.k1));
+      axpy2_kernel<<<nblk, 256, 0, s>>>(p.x, -(t - r), 1.0f, p.k1, 0.f, nullptr, p.x, n);
+      count_launch();
+    }
+  }
+  unpad_rows_kernel<<<blocks_for(B * d.D, 256), 256, 0, s>>>(p.x, d.Dp, out, d.D, B);
+  count_launch();
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,575 @@
+// Row kernels and fused GEMM epilogues of the iMF step (everything that is not a tcgen05 MMA).
+//
+// Reference semantics (paths inside /root/reference/meanflow_audio_codec/):
+//   time embedding        utils.py:5-13
+//   (t, r) sampling       utils.py:32-45
+//   z_t / target          trainers/noise_schedules.py:69-88
+//   block (AdaLN + MLP)   models/mlp_flow.py:83-117
+//   tangent recurrences   jax.jvp at trainers/loss_strategies.py:263-267
+//   loss                  utils.py:16-25, loss_strategies.py:270-277
+//   backward recurrences  jax.value_and_grad at loss_strategies.py:279
+#pragma once
+
+#include "imf_layout.cuh"
+
+namespace mfac {
+
+constexpr float LN_EPS = 1e-6f;
+constexpr int ROW_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (own stream; the reference's threefry stream is not imitated,
+// parity runs pass e/t/r explicitly -- SURVEY.md R6)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
+// 4 x N(0,1) for counter (idx, stream, step)
+__device__ __forceinline__ float4 philox_normal4(uint64_t idx, uint32_t stream, uint64_t seed, uint64_t step) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), stream ^ (uint32_t)(step << 8), (uint32_t)(step >> 24)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+  float s0, c0, s1, c1;
+  sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+  sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// cond[j] = cos(t f_j) + cos(h f_j), cond[half+j] = sin(t f_j) + sin(h f_j); optional d/ds along (tdot=1,hdot=1)
+__device__ __forceinline__ void write_cond_row(float t, float h, int C, int Cp, __nv_bfloat16* cond, __nv_bfloat16* dcond) {
+  const int half = C / 2;
+  for (int j = threadIdx.x; j < Cp; j += blockDim.x) {
+    float v = 0.f, dv = 0.f;
+    if (j < C) {
+      const int q = j < half ? j : j - half;
+      const float f = expf(-9.210340371976184f * (float)q / (float)half);
+      float st, ct, sh, ch;
+      sincosf(t * f, &st, &ct);
+      sincosf(h * f, &sh, &ch);
+      if (j < half) { v = ct + ch; dv = -f * (st + sh); }
+      else { v = st + sh; dv = f * (ct + ch); }
+    }
+    cond[j] = __float2bfloat16(v);
+    if (dcond) dcond[j] = __float2bfloat16(dv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// iMF prologue: one block per row.  e, t, r drawn or copied; z_t; bf16 copy of x; three cond rows.
+// ---------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float* x;      // [B, D]
+  const float* e_in;   // [B, D] or null
+  const float* t_in;   // [B] or null
+  const float* r_in;   // [B] or null
+  float* e;            // [B, Dp]
+  float* z;            // [B, Dp]
+  __nv_bfloat16* xb;   // [B, Dp]
+  float* t;            // [B]
+  float* r;            // [B]
+  __nv_bfloat16 *cond_v, *cond_u, *dcond_u;  // [B, Cp]
+  MfacImfConfig cfg;
+  int64_t B;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims d) {
+  const int64_t b = blockIdx.x;
+  __shared__ float s_tr[2];
+  if (threadIdx.x == 0) {
+    float t, r;
+    if (a.t_in) {
+      t = a.t_in[b];
+      r = a.r_in[b];
+    } else {
+      const float4 n4 = philox_normal4(a.cfg.row_offset + b, 1u, a.cfg.seed, a.cfg.step);
+      const float lt = 1.0f / (1.0f + expf(-(n4.x * a.cfg.time_std + a.cfg.time_mean)));
+      const float lr = 1.0f / (1.0f + expf(-(n4.y * a.cfg.time_std + a.cfg.time_mean)));
+      t = fmaxf(lt, lr);
+      r = fminf(lt, lr);
+      if (b < (int64_t)((float)a.B * a.cfg.data_proportion)) r = t;  // utils.py:41-44, per local shard
+    }
+    s_tr[0] = t; s_tr[1] = r;
+    a.t[b] = t; a.r[b] = r;
+  }
+  __syncthreads();
+  const float t = s_tr[0], r = s_tr[1];
+  const float nscale = a.cfg.noise_min + a.cfg.noise_max * t;
+  for (int j4 = threadIdx.x * 4; j4 < d.Dp; j4 += blockDim.x * 4) {
+    float ev[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!a.e_in && j4 < d.D) {
+      const uint64_t idx = ((a.cfg.row_offset + (uint64_t)b) * (uint64_t)d.Dp + (uint64_t)j4) >> 2;
+      const float4 n4 = philox_normal4(idx, 0u, a.cfg.seed, a.cfg.step);
+      ev[0] = n4.x; ev[1] = n4.y; ev[2] = n4.z; ev[3] = n4.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j4 + q;
+      float xv = 0.f, e = 0.f;
+      if (j < d.D) {
+        xv = a.x[b * d.D + j];
+        e = a.e_in ? a.e_in[b * d.D + j] : ev[q];
+      }
+      a.e[b * d.Dp + j] = e;
+      a.z[b * d.Dp + j] = (1.0f - t) * xv + nscale * e;
+      a.xb[b * d.Dp + j] = __float2bfloat16(xv);
+    }
+  }
+  write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + b * d.Cp, nullptr);
+  write_cond_row(t, t - r, d.C, d.Cp, a.cond_u + b * d.Cp, a.dcond_u + b * d.Cp);
+}
+
+// time[B,2] -> cond[B,Cp]   (mfac_mlp_forward / samplers)
+__global__ void __launch_bounds__(128) cond_from_time_kernel(const float* time, __nv_bfloat16* cond, Dims d) {
+  const int64_t b = blockIdx.x;
+  write_cond_row(time[2 * b], time[2 * b + 1], d.C, d.Cp, cond + b * d.Cp, nullptr);
+}
+// constant (t, h) for every row (samplers)
+__global__ void __launch_bounds__(128) cond_const_kernel(float t, float h, __nv_bfloat16* cond, Dims d) {
+  const int64_t b = blockIdx.x;
+  write_cond_row(t, h, d.C, d.Cp, cond + b * d.Cp, nullptr);
+}
+
+// fp32 [B, n] -> padded fp32 [B, np] and/or bf16 [B, np]
+__global__ void pad_rows_kernel(const float* src, int n, float* dst_f, __nv_bfloat16* dst_b, int np, int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * np) return;
+  const int64_t b = i / np;
+  const int j = (int)(i % np);
+  const float v = j < n ? src[b * n + j] : 0.f;
+  if (dst_f) dst_f[i] = v;
+  if (dst_b) dst_b[i] = __float2bfloat16(v);
+}
+__global__ void unpad_rows_kernel(const float* src, int np, float* dst, int n, int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const int64_t b = i / n;
+  const int j = (int)(i % n);
+  dst[i] = src[b * np + j];
+}
+
+// ---------------------------------------------------------------------------------------
+// AdaLN: n = LN([lat|x]) (no affine, eps 1e-6, var = max(0, E[c^2]-mu^2)); hin = (1+s1) n + shift.
+// TANGENT adds cdot = [0|xdot]: ndot = (cdot - mean(cdot) - n mean(n cdot)) rstd;
+//                               hindot = s1dot n + (1+s1) ndot + shiftdot.
+// One block per row; the row is staged in shared memory (any Ip).
+// ---------------------------------------------------------------------------------------
+struct LnModArgs {
+  const float* lat;          // [B, Lp] or null (zeros)
+  const float* x;            // [B, Dp]
+  const __nv_bfloat16* m;    // [B, Mp]
+  __nv_bfloat16* hin;        // [B, Ip]
+  const float* xd;           // tangent
+  const __nv_bfloat16* md;   // tangent
+  __nv_bfloat16* hind;       // tangent
+  float* mu;                 // [B] or null
+  float* rstd;               // [B] or null
+};
+
+template <bool TANGENT>
+__global__ void __launch_bounds__(ROW_THREADS) lnmod_kernel(LnModArgs a, Dims d) {
+  extern __shared__ float s_row[];  // c[Ip] (+ cd[Ip])
+  __shared__ float red[32];
+  float* s_c = s_row;
+  float* s_cd = s_row + d.Ip;
+  const int64_t b = blockIdx.x;
+  float sum = 0.f, sq = 0.f, sumd = 0.f;
+  for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
+    float c = 0.f, cd = 0.f;
+    if (p < d.Lp) {
+      if (a.lat && p < d.L) c = a.lat[b * d.Lp + p];
+    } else if (p - d.Lp < d.D) {
+      c = a.x[b * d.Dp + (p - d.Lp)];
+      if (TANGENT) cd = a.xd[b * d.Dp + (p - d.Lp)];
+    }
+    s_c[p] = c;
+    sum += c;
+    sq += c * c;
+    if (TANGENT) { s_cd[p] = cd; sumd += cd; }
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float mu = block_sum(sum, red) * inv_i;
+  const float ex2 = block_sum(sq, red) * inv_i;
+  const float rstd = rsqrtf(fmaxf(0.f, ex2 - mu * mu) + LN_EPS);
+  float mean_cd = 0.f, mean_ncd = 0.f;
+  if (TANGENT) {
+    mean_cd = block_sum(sumd, red) * inv_i;
+    float acc = 0.f;
+    for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
+      const bool real = p < d.L || (p >= d.Lp && p - d.Lp < d.D);
+      if (real) acc += (s_c[p] - mu) * rstd * s_cd[p];
+    }
+    mean_ncd = block_sum(acc, red) * inv_i;
+  }
+  if (threadIdx.x == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
+  const __nv_bfloat16* mrow = a.m + b * d.Mp;
+  const __nv_bfloat16* mdrow = TANGENT ? a.md + b * d.Mp : nullptr;
+  for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
+    const bool real = p < d.L || (p >= d.Lp && p - d.Lp < d.D);
+    float h = 0.f, hd = 0.f;
+    if (real) {
+      const float n = (s_c[p] - mu) * rstd;
+      const float s1 = __bfloat162float(mrow[p]), sh = __bfloat162float(mrow[d.Ip + p]);
+      h = (1.0f + s1) * n + sh;
+      if (TANGENT) {
+        const float nd = (s_cd[p] - mean_cd - n * mean_ncd) * rstd;
+        hd = __bfloat162float(mdrow[p]) * n + (1.0f + s1) * nd + __bfloat162float(mdrow[d.Ip + p]);
+      }
+    }
+    a.hin[b * d.Ip + p] = __float2bfloat16(h);
+    if (TANGENT) a.hind[b * d.Ip + p] = __float2bfloat16(hd);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// loss: delta = u + (t-r) dudt - (nmax e - x);  s_b = sum delta^2;  w_b = 1/(s_b + c)
+//       g_u = 2 w_b delta / B   (weighted)   or   2 delta / (B D)   (plain MSE)
+// ---------------------------------------------------------------------------------------
+struct LossArgs {
+  const float *u, *dudt, *e;  // [B, Dp]
+  const float* x;             // [B, D]
+  const float *t, *r;         // [B]
+  float* g_x;                 // [B, Dp]
+  float* row_loss;            // [B]
+  float* per_example;         // [B] or null
+  MfacImfConfig cfg;
+  int64_t B;
+};
+__global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims d) {
+  extern __shared__ float s_delta[];  // [Dp]
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const float tr = a.t[b] - a.r[b];
+  float sq = 0.f;
+  for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) {
+    float dl = 0.f;
+    if (j < d.D) {
+      const int64_t i = b * d.Dp + j;
+      const float vpred = a.u[i] + tr * a.dudt[i];
+      dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
+    }
+    s_delta[j] = dl;
+    sq += dl * dl;
+  }
+  const float s = block_sum(sq, red);
+  float w, rl;
+  if (a.cfg.use_weighted_loss) {
+    w = 1.0f / (s + a.cfg.loss_c);
+    rl = w * s / (float)a.B;
+    w = 2.0f * w / (float)a.B;
+  } else {
+    rl = s / ((float)a.B * (float)d.D);
+    w = 2.0f / ((float)a.B * (float)d.D);
+  }
+  if (threadIdx.x == 0) {
+    a.row_loss[b] = rl;
+    if (a.per_example) a.per_example[b] = s;
+  }
+  for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) a.g_x[b * d.Dp + j] = w * s_delta[j];
+}
+// deterministic sum of row_loss[B] -> loss
+__global__ void __launch_bounds__(1024) sum_rows_kernel(const float* v, int64_t n, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// backward elementwise pieces
+// ---------------------------------------------------------------------------------------
+// g_o = g_x (1+s2)/nb  (bf16, GEMM operand);  g_s2 = g_x o / nb -> g_m[:, 2Ip:]
+__global__ void bwd_block_out_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o, __nv_bfloat16* g_o,
+                                     __nv_bfloat16* g_m, Dims d, int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d.Dp) return;
+  const int64_t b = i / d.Dp;
+  const int j = (int)(i % d.Dp);
+  const float inv_nb = 1.0f / (float)d.nb;
+  const float g = g_x[i];
+  const float s2 = __bfloat162float(m[b * d.Mp + 2 * d.Ip + j]);
+  g_o[i] = __float2bfloat16(g * (1.0f + s2) * inv_nb);
+  g_m[b * d.Mp + 2 * d.Ip + j] = __float2bfloat16(g * __bfloat162float(o[i]) * inv_nb);
+}
+
+// LayerNorm / modulation backward, one block per row.
+struct LnBwdArgs {
+  const float* g_hin;       // [B, Ip]
+  const float* lat;         // [B, Lp]
+  const float* x;           // [B, Dp]  block input
+  const float *mu, *rstd;   // [B]
+  const __nv_bfloat16* m;   // [B, Mp]
+  __nv_bfloat16* g_m;       // [B, Mp]  writes [0, 2Ip)
+  float* g_lat;             // [B, Lp]  +=
+  float* g_x;               // [B, Dp]  +=
+};
+__global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a, Dims d) {
+  extern __shared__ float s_row[];  // n[Ip], g_n[Ip]
+  __shared__ float red[32];
+  float* s_n = s_row;
+  float* s_gn = s_row + d.Ip;
+  const int64_t b = blockIdx.x;
+  const float mu = a.mu[b], rstd = a.rstd[b];
+  float s1sum = 0.f, s2sum = 0.f;
+  for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
+    const bool real = p < d.L || (p >= d.Lp && p - d.Lp < d.D);
+    float n = 0.f, gn = 0.f, gh = 0.f;
+    if (real) {
+      const float c = p < d.Lp ? a.lat[b * d.Lp + p] : a.x[b * d.Dp + (p - d.Lp)];
+      n = (c - mu) * rstd;
+      gh = a.g_hin[b * d.Ip + p];
+      gn = gh * (1.0f + __bfloat162float(a.m[b * d.Mp + p]));
+    }
+    s_n[p] = n;
+    s_gn[p] = gn;
+    s1sum += gn;
+    s2sum += gn * n;
+    a.g_m[b * d.Mp + p] = __float2bfloat16(gh * n);          // g_s1
+    a.g_m[b * d.Mp + d.Ip + p] = __float2bfloat16(gh);       // g_shift
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float m1 = block_sum(s1sum, red) * inv_i;
+  const float m2 = block_sum(s2sum, red) * inv_i;
+  for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
+    const bool real = p < d.L || (p >= d.Lp && p - d.Lp < d.D);
+    if (!real) continue;
+    const float gc = (s_gn[p] - m1 - s_n[p] * m2) * rstd;
+    if (p < d.Lp) a.g_lat[b * d.Lp + p] += gc;
+    else a.g_x[b * d.Dp + (p - d.Lp)] += gc;
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
+// Column sums of a bf16 [B, ld] matrix, deterministic two-stage.
+// stage 1: grid (ld/64, R) blocks of 256 threads; partial[r][ld]
+constexpr int COLSUM_ROWS = 512;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* partial) {
+  __shared__ float2 s_red[8][32];
+  const int cpair = threadIdx.x & 31, rlane = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + cpair * 2;
+  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_ROWS;
+  const int64_t r1 = min(B, r0 + COLSUM_ROWS);
+  float2 acc = make_float2(0.f, 0.f);
+  for (int64_t r = r0 + rlane; r < r1; r += 8) {
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(G + r * ld + col));
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  s_red[rlane][cpair] = acc;
+  __syncthreads();
+  if (rlane == 0) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { acc.x += s_red[q][cpair].x; acc.y += s_red[q][cpair].y; }
+    partial[(int64_t)blockIdx.y * ld + col] = acc.x;
+    partial[(int64_t)blockIdx.y * ld + col + 1] = acc.y;
+  }
+}
+// stage 2: out[map(col)] = sum_r partial[r][col]; kind selects the padded->real column map
+enum ColMap { MAP_ID = 0, MAP_CM = 1, MAP_MM = 2 };
+__device__ __forceinline__ int map_col(int kind, int p, int limit, const Dims& d) {
+  if (kind == MAP_CM) return d.cm_inv(p);
+  if (kind == MAP_MM) return d.mm_inv(p);
+  return p < limit ? p : -1;
+}
+__global__ void colsum_final_kernel(const float* partial, int ld, int R, float* out, int kind, int limit, Dims d) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ld) return;
+  const int c = map_col(kind, p, limit, d);
+  if (c < 0) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += partial[(int64_t)r * ld + p];
+  out[c] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// sampler elementwise updates on padded [B, Dp] fp32 buffers
+// ---------------------------------------------------------------------------------------
+// out = a + alpha * (g1 * k1 + g2 * k2)     (a and k2 may be null)
+__global__ void axpy2_kernel(const float* a, float alpha, float g1, const float* k1, float g2, const float* k2, float* out,
+                             int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = g1 * k1[i];
+  if (k2) v += g2 * k2[i];
+  out[i] = (a ? a[i] : 0.f) + alpha * v;
+}
+__global__ void fill_normal_kernel(float* out, int Dp, int D, int64_t B, uint64_t seed) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= B * Dp) return;
+  const float4 n4 = philox_normal4((uint64_t)(i4 >> 2), 7u, seed, 0);
+  const float v[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[i4 + q] = ((int)((i4 + q) % Dp) < D) ? v[q] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused GEMM epilogues: operator()(row, col0, acc[32]) with thread == output row
+// ---------------------------------------------------------------------------------------
+// g = gelu(acc + bias); optionally keeps the pre-activation a (bf16) for the tangent/backward.
+struct EpiBiasGelu {
+  const float* bias;        // padded fp32 [N]
+  __nv_bfloat16* g;         // [M, ld]
+  __nv_bfloat16* a_out;     // [M, ld] or null
+  int64_t ld;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    float bv[32];
+    load_f32x32(bias + col0, bv);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += bv[j];
+    if (a_out) store_bf16x32(a_out + (int64_t)row * ld + col0, acc);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = gelu_tanh(acc[j]);
+    store_bf16x32(g + (int64_t)row * ld + col0, acc);
+  }
+};
+// out = acc * gelu'(a)   (tangent through GELU, and the backward of GELU)
+struct EpiMulDgelu {
+  const __nv_bfloat16* a;   // [M, ld]
+  __nv_bfloat16* out;       // [M, ld]
+  int64_t ld;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    float av[32];
+    load_bf16x32(a + (int64_t)row * ld + col0, av);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= dgelu_tanh(av[j]);
+    store_bf16x32(out + (int64_t)row * ld + col0, acc);
+  }
+};
+// out = acc (+ bias)
+struct EpiLinearBf16 {
+  const float* bias;  // or null
+  __nv_bfloat16* out;
+  int64_t ld;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    if (bias) {
+      float bv[32];
+      load_f32x32(bias + col0, bv);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += bv[j];
+    }
+    store_bf16x32(out + (int64_t)row * ld + col0, acc);
+  }
+};
+struct EpiLinearF32 {
+  const float* bias;  // or null
+  float* out;
+  int64_t ld;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    if (bias) {
+      float bv[32];
+      load_f32x32(bias + col0, bv);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += bv[j];
+    }
+    store_f32x32(out + (int64_t)row * ld + col0, acc);
+  }
+};
+// block output: o = acc + b2;  x_new = o (1 + s2) / nb + x_old      (mlp_flow.py:112-117)
+struct EpiBlockOut {
+  const float* bias;          // padded [Dp]
+  const __nv_bfloat16* m;     // [M, Mp]; s2 at column offset s2_off
+  const float* x_old;         // [M, Dp]
+  float* x_new;               // [M, Dp] (may alias x_old)
+  __nv_bfloat16* o_out;       // [M, Dp] or null
+  int64_t ldm, ldx;
+  int s2_off;
+  float inv_nb;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    float t[32];
+    load_f32x32(bias + col0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += t[j];
+    if (o_out) store_bf16x32(o_out + (int64_t)row * ldx + col0, acc);
+    load_bf16x32(m + (int64_t)row * ldm + s2_off + col0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= (1.0f + t[j]) * inv_nb;
+    load_f32x32(x_old + (int64_t)row * ldx + col0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += t[j];
+    store_f32x32(x_new + (int64_t)row * ldx + col0, acc);
+  }
+};
+// tangent of the block output: xd_new = (od (1+s2) + o s2d) / nb + xd_old
+struct EpiBlockOutTangent {
+  const __nv_bfloat16* m;     // primal modulation  [M, Mp]
+  const __nv_bfloat16* md;    // tangent modulation [M, Mp]
+  const __nv_bfloat16* o;     // primal o [M, Dp]
+  const float* xd_old;
+  float* xd_new;
+  int64_t ldm, ldx;
+  int s2_off;
+  float inv_nb;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    float t[32], q[32];
+    load_bf16x32(m + (int64_t)row * ldm + s2_off + col0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= (1.0f + t[j]);
+    load_bf16x32(md + (int64_t)row * ldm + s2_off + col0, t);
+    load_bf16x32(o + (int64_t)row * ldx + col0, q);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + q[j] * t[j]) * inv_nb;
+    load_f32x32(xd_old + (int64_t)row * ldx + col0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += t[j];
+    store_f32x32(xd_new + (int64_t)row * ldx + col0, acc);
+  }
+};
+// weight gradient: padded (row, col) -> flat fp32 [rows_real, cols_real] with inverse maps
+struct EpiGradStore {
+  float* G;       // leaf base in the flat gradient
+  int ld;         // real number of columns
+  int row_kind, row_limit, col_kind, col_limit;
+  Dims d;
+  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+    const int r = map_col(row_kind, row, row_limit, d);
+    if (r < 0) return;
+    float* dst = G + (int64_t)r * ld;
+    const int c0 = map_col(col_kind, col0, col_limit, d);
+    const int c31 = map_col(col_kind, col0 + 31, col_limit, d);
+    if (c0 >= 0 && c31 == c0 + 31) {
+      float* p = dst + c0;
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        store_f32x32(p, acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p[j] = acc[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = map_col(col_kind, col0 + j, col_limit, d);
+        if (c >= 0) dst[c] = acc[j];
+      }
+    }
+  }
+};
+
+}  // namespace mfac

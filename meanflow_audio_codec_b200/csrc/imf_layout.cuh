@@ -28,6 +28,9 @@ struct Dims {
   int64_t o_e1b, o_e1w, o_e2b, o_e2w, total;
   // bf16 shadow offsets (elements) inside one block, block stride, encoder offsets, total
   int64_t s_c1w, s_c2w, s_m1w, s_m2w, s_blk_stride, s_e1w, s_e2w, s_total;
+  // padded fp32 bias offsets (elements) inside the bias section of the shadow
+  int64_t b_c1, b_c2, b_m1, b_m2, b_blk_stride, b_e1, b_e2, b_total;
+  int64_t bias_section_bytes_offset;  // byte offset of the fp32 bias section inside the shadow buffer
 
   __host__ __device__ int cm(int j) const { return j < L ? j : Lp + (j - L); }
   // padded concat column -> real column or -1
@@ -93,53 +96,67 @@ inline int make_dims(const MfacMlpDims* d, Dims* out) {
   x.s_e1w = take((int64_t)x.Dp * x.Hep);
   x.s_e2w = take((int64_t)x.Hep * x.Lp);
   x.s_total = s;
+  int64_t bo = 0;
+  auto takeb = [&](int64_t n) { int64_t at = bo; bo += round_up<int64_t>(n, 64); return at; };
+  x.b_c1 = takeb(x.Cp);
+  x.b_c2 = takeb(x.Mp);
+  x.b_m1 = takeb(x.Ip);
+  x.b_m2 = takeb(x.Dp);
+  x.b_blk_stride = bo;
+  bo = x.b_blk_stride * x.nb;
+  x.b_e1 = takeb(x.Hep);
+  x.b_e2 = takeb(x.Lp);
+  x.b_total = bo;
+  x.bias_section_bytes_offset = round_up<int64_t>(x.s_total * 2, 256);
   *out = x;
   return MFAC_SUCCESS;
 }
 
-// Maps a flat parameter index to its leaf and (row, col); returns the bf16 shadow element index for
-// kernel leaves (or -1 for biases).  Used by the cast and AdamW kernels.
-__host__ __device__ inline int64_t shadow_index_of(const Dims& d, int64_t i) {
-  int64_t base_s;
-  int64_t w;  // offset inside the block / encoder
+// Maps a flat parameter index to its slot in the shadow: kernels -> bf16 element index in the weight
+// section, biases -> fp32 element index in the bias section.  Used by the cast and AdamW kernels.
+struct ShadowSlot {
+  int64_t idx;
+  bool is_bias;
+};
+__host__ __device__ inline ShadowSlot shadow_slot_of(const Dims& d, int64_t i) {
   if (i < d.blk_stride * d.nb) {
     const int64_t k = i / d.blk_stride;
-    w = i - k * d.blk_stride;
-    base_s = k * d.s_blk_stride;
-    if (w < d.o_c1w) return -1;
+    const int64_t w = i - k * d.blk_stride;
+    const int64_t base_s = k * d.s_blk_stride, base_b = k * d.b_blk_stride;
+    if (w < d.o_c1w) return {base_b + d.b_c1 + (w - d.o_c1b), true};
     if (w < d.o_c2b) {
       const int64_t q = w - d.o_c1w;
-      const int r = (int)(q / d.C), c = (int)(q % d.C);
-      return base_s + d.s_c1w + (int64_t)r * d.Cp + c;
+      const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.C), c = (int)(qq % (uint32_t)d.C);
+      return {base_s + d.s_c1w + (int64_t)r * d.Cp + c, false};
     }
-    if (w < d.o_c2w) return -1;
+    if (w < d.o_c2w) return {base_b + d.b_c2 + d.mm((int)(w - d.o_c2b)), true};
     if (w < d.o_m1b) {
       const int64_t q = w - d.o_c2w;
       const int W = 2 * d.I + d.D;
-      const int r = (int)(q / W), c = (int)(q % W);
-      return base_s + d.s_c2w + (int64_t)r * d.Mp + d.mm(c);
+      const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)W), c = (int)(qq % (uint32_t)W);
+      return {base_s + d.s_c2w + (int64_t)r * d.Mp + d.mm(c), false};
     }
-    if (w < d.o_m1w) return -1;
+    if (w < d.o_m1w) return {base_b + d.b_m1 + d.cm((int)(w - d.o_m1b)), true};
     if (w < d.o_m2b) {
       const int64_t q = w - d.o_m1w;
-      const int r = (int)(q / d.I), c = (int)(q % d.I);
-      return base_s + d.s_m1w + (int64_t)d.cm(r) * d.Ip + d.cm(c);
+      const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.I), c = (int)(qq % (uint32_t)d.I);
+      return {base_s + d.s_m1w + (int64_t)d.cm(r) * d.Ip + d.cm(c), false};
     }
-    if (w < d.o_m2w) return -1;
+    if (w < d.o_m2w) return {base_b + d.b_m2 + (w - d.o_m2b), true};
     const int64_t q = w - d.o_m2w;
-    const int r = (int)(q / d.D), c = (int)(q % d.D);
-    return base_s + d.s_m2w + (int64_t)d.cm(r) * d.Dp + c;
+    const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.D), c = (int)(qq % (uint32_t)d.D);
+    return {base_s + d.s_m2w + (int64_t)d.cm(r) * d.Dp + c, false};
   }
-  if (i < d.o_e1w) return -1;
+  if (i < d.o_e1w) return {d.b_e1 + (i - d.o_e1b), true};
   if (i < d.o_e2b) {
     const int64_t q = i - d.o_e1w;
-    const int r = (int)(q / d.He), c = (int)(q % d.He);
-    return d.s_e1w + (int64_t)r * d.Hep + c;
+    const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.He), c = (int)(qq % (uint32_t)d.He);
+    return {d.s_e1w + (int64_t)r * d.Hep + c, false};
   }
-  if (i < d.o_e2w) return -1;
+  if (i < d.o_e2w) return {d.b_e2 + (i - d.o_e2b), true};
   const int64_t q = i - d.o_e2w;
-  const int r = (int)(q / d.L), c = (int)(q % d.L);
-  return d.s_e2w + (int64_t)r * d.Lp + c;
+  const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.L), c = (int)(qq % (uint32_t)d.L);
+  return {d.s_e2w + (int64_t)r * d.Lp + c, false};
 }
 
 // Simple bump allocator over the caller-provided workspace (256-byte aligned slices).
