@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- iMF training throughput (samples/s) of the B200-native hot path, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mfac|reference] [--batch B] [--noise-dimension T]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one full training step of the reference's hot loop (trainers/train.py:333-347) on one
+batch of synthetic audio: MDCT tokenisation -> ImprovedMeanFlowLoss.compute_loss (v pass, u pass +
+JVP, loss, backward) -> gradient all-reduce (N > 1) -> AdamW.  Workload = BASELINE.json configs[1]
+(method=improved_mean_flow, architecture=mlp, dataset=audio, tokenization=mdct) with the substitution
+SURVEY.md R4 forces: the shipped noise_dimension=196608 needs 309 G parameters per block and cannot be
+instantiated anywhere, so noise_dimension is a flag (default 784 samples -> 2 MDCT frames -> D=1024, the
+geometry of the one runnable config); every other hyper-parameter is the config's.  The per-GPU batch is
+a flag too: the config's batch_size=128 is launch/optimizer-bound on a B200, so the default is the
+tensor-bound 4096 and the config-faithful 128 is reported next to it under "sweep".
+
+Keys beyond the base contract: "roofline" (tcgen05 GEMM family, per-launch CUDA events), "cpu_baseline"
+(oracle port on the host cores), "e2e" (host buffers through the public Python API), "clocks", "codec"
+(MDCT -> encode -> 1-NFE mean-flow sample -> IMDCT audio-seconds/s at 1 GPU), "sweep".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG = dict(condition_dimension=128, latent_dimension=256, num_blocks=8, base_lr=1e-4, weight_decay=1e-4,
+           window_size=512, hop_size=256, seed=42)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d["bf16_tflops_sustained"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def token_dim(T: int) -> tuple[int, int]:
+    N, hop = CFG["window_size"], CFG["hop_size"]
+    nf = 1 if T < N else (T - N) // hop + 1
+    return nf, nf * N
+
+
+def flops_per_sample(D: int) -> float:
+    """B * (3 * 2 * P_enc + 5 * 2 * P_dec) GEMM FLOPs."""
+    L, C, nb = CFG["latent_dimension"], CFG["condition_dimension"], CFG["num_blocks"]
+    I, He = L + D, (D + L) // 2
+    p_enc = D * He + He * L
+    p_dec = nb * (C * C + C * (2 * I + D) + I * I + I * D)
+    return 3 * 2 * p_enc + 5 * 2 * p_dec
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_factory(T: int, B: int):
+    """The reference's CPU path for one step, restated (oracle/): MDCT tokenisation -> iMF loss+grads -> AdamW.
+    JAX is not installable in this image (no wheel, no network), so this is the torch-CPU port ("kind": "port")."""
+    import numpy as np
+    import torch
+    from oracle import imf_np, imf_torch, mdct_np
+    nf, D = token_dim(T)
+    p = {k: torch.from_numpy(v) for k, v in imf_np.init_params(D, CFG["latent_dimension"], CFG["condition_dimension"],
+                                                               CFG["num_blocks"], seed=CFG["seed"]).items()}
+    mu = {k: torch.zeros_like(v) for k, v in p.items()}
+    nu = {k: torch.zeros_like(v) for k, v in p.items()}
+    g = torch.Generator().manual_seed(42)
+    x_raw = (0.1 * torch.randn(B, T, generator=g)).numpy()
+    w = torch.from_numpy(mdct_np.window_2n(CFG["window_size"], np.float32))
+    Cb = torch.from_numpy(mdct_np.cosine_basis(CFG["window_size"], np.float32))
+    N, hop = CFG["window_size"], CFG["hop_size"]
+    state = {"count": 0}
+
+    def step():
+        xr = torch.from_numpy(x_raw)
+        need = (nf - 1) * hop + 2 * N
+        xr = torch.nn.functional.pad(xr, (0, max(0, need - T)))
+        tok = torch.stack([(xr[:, i * hop:i * hop + 2 * N] * w) @ Cb for i in range(nf)], 1).reshape(B, D)
+        e = torch.randn(B, D, generator=g)
+        n2 = torch.randn(2, B, generator=g)
+        t = torch.sigmoid(n2[0] - 0.4); r = torch.sigmoid(n2[1] - 0.4)
+        t, r = torch.maximum(t, r), torch.minimum(t, r)
+        r = torch.where(torch.arange(B) < B // 2, t, r)
+        loss, grads, _ = imf_torch.imf_loss_and_grads(p, tok, e, t[:, None], r[:, None])
+        imf_torch.adamw_step(p, grads, mu, nu, state["count"], lr=CFG["base_lr"], wd=CFG["weight_decay"])
+        state["count"] += 1
+        return float(loss)
+
+    return step
+
+
+def time_cpu_reference(T: int, B: int, steps: int, warmup: int, budget_s: float = 25.0):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_factory(T, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=B * done / dt, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{done} steps of batch {B} (torch-CPU restatement of the reference step, fp32, T={T})",
+                ms_per_step=dt / done * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nf, D = token_dim(args.noise_dimension)
+    B = min(args.batch, 256)
+    cb = time_cpu_reference(args.noise_dimension, B, max(1, args.steps), min(args.warmup, 1), budget_s=90.0)
+    line = {
+        "metric": "imf_train_samples_per_sec", "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": workload_config(args, B, D, nf),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, B, D, nf):
+    return {
+        "workload": (f"imf_train_step method=improved_mean_flow architecture=mlp dataset=audio(synthetic 0.1*randn) "
+                     f"tokenization=mdct(N=512,hop=256) noise_dimension={args.noise_dimension}->nf={nf},D={D} "
+                     f"L=256 C=128 blocks=8 per_gpu_batch={B}"),
+        "substitution": "config noise_dimension=196608 is not instantiable (SURVEY.md R4); batch_size=128 reported under sweep",
+        "global_batch": B * args.gpus, "per_gpu_batch": B, "parallelism": f"dp{args.gpus}",
+        "l2": "working set per step (fp32 params+grads+AdamW moments+activations) exceeds the 126 MB L2",
+    }
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_mfac(args):
+    import torch
+    import meanflow_audio_codec_b200 as m
+    from meanflow_audio_codec_b200 import _lib
+    from meanflow_audio_codec_b200.data_parallel import DataParallel, train_step_dp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl mfac needs a CUDA device (no CPU fallback)")
+    dp = DataParallel()
+    world, rank = dp.world, dp.rank
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(dp.local_rank)
+    dev = torch.device("cuda", dp.local_rank)
+    T = args.noise_dimension
+    nf, D = token_dim(T)
+    pk = peaks()
+
+    def make(B):
+        model = m.ConditionalFlow(noise_dimension=D, condition_dimension=CFG["condition_dimension"],
+                                  num_blocks=CFG["num_blocks"], latent_dimension=CFG["latent_dimension"])
+        params = model.init(CFG["seed"], device=dev)["params"]  # same weights on every rank
+        state = m.TrainState.create(apply_fn=model.apply, params=params, tx=m.adamw(CFG["base_lr"], CFG["weight_decay"]))
+        strat = m.ImprovedMeanFlowLoss(m.LinearNoiseSchedule(0.001, 0.999), m.MeanFlowTimeSampling(-0.4, 1.0, 0.5), True)
+        tok = m.MDCTTokenization(window_size=CFG["window_size"], hop_size=CFG["hop_size"])
+        g = torch.Generator(device=dev).manual_seed(42 + rank)
+        x_raw = 0.1 * torch.randn(B, T, device=dev, generator=g)
+        return model, state, strat, tok, x_raw
+
+    def step_fn(state, strat, tok, x_raw, key=0):
+        x = tok.tokenize(x_raw).reshape(x_raw.shape[0], -1)
+        state, loss, _ = train_step_dp(dp, state, key, x, strat)
+        return state, loss
+
+    def timed(B, steps, warmup, sample_clocks=False):
+        model, state, strat, tok, x_raw = make(B)
+        for _ in range(warmup):
+            state, loss = step_fn(state, strat, tok, x_raw)
+        torch.cuda.synchronize()
+        dp.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(dp.local_rank) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            state, loss = step_fn(state, strat, tok, x_raw)
+        e1.record()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        dp.barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
+        launches = (_lib.launches() - l0) / steps
+        return dict(ms_total=ms, ms_per_step=ms / steps, wall_ms=(w1 - w0) * 1e3, launches=launches, loss=float(loss),
+                    clocks=sampler.summary() if sampler else None, objs=(model, state, strat, tok, x_raw))
+
+    B = args.batch
+    main = timed(B, args.steps, args.warmup, sample_clocks=True)
+    value = B * world * args.steps / (main["ms_total"] * 1e-3)
+    model, state, strat, tok, x_raw = main["objs"]
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D of the raw audio + D2H of the loss per step
+    x_host = x_raw.cpu().pin_memory()
+    for _ in range(2):
+        state, loss = step_fn(state, strat, tok, x_host.to(dev, non_blocking=True))
+        float(loss)
+    torch.cuda.synchronize(); dp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        state, loss = step_fn(state, strat, tok, xd)
+        lv = float(loss)  # device -> host read every step, like trainers/train.py:347
+    torch.cuda.synchronize()
+    e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
+    dp.barrier()
+    e2e = {"value": B * world * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+           "d2h_bytes_per_step": 4, "api": "MDCTTokenization.tokenize + train_step (ImprovedMeanFlowLoss) on pinned host input"}
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): per-launch CUDA events on the launch stream
+    roofline, families = None, None
+    if True:
+        _lib.profile_enable(True)
+        nprof = max(1, min(3, args.steps))
+        for _ in range(nprof):
+            state, loss = step_fn(state, strat, tok, x_raw)
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+        gm = prof["gemm_tcgen05"]
+        if gm["launches"]:
+            achieved = gm["work"] / (gm["ms"] * 1e-3) / 1e12
+            traffic = None
+            tf = ROOT / "profiles" / "ncu_traffic.json"
+            if tf.exists():
+                try:
+                    traffic = json.loads(tf.read_text()).get("gemm_tcgen05_dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all fused-epilogue instantiations)",
+                        "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
+                        "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                        "launches_per_step": gm["launches"] / nprof, "ms_per_step_in_kernel": gm["ms"] / nprof,
+                        "share_of_step": gm["ms"] / nprof / main["ms_per_step"],
+                        "flops_per_step_measured": gm["work"] / nprof, "flops_per_step_survey": flops_per_sample(D) * B}
+        families = {k: {"launches_per_step": v["launches"] / nprof, "ms_per_step": v["ms"] / nprof,
+                        "achieved": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k == "gemm_tcgen05" else 1e9)) if v["ms"] > 0 else None,
+                        "unit": "TFLOP/s" if k == "gemm_tcgen05" else "GB/s"} for k, v in prof.items() if v["launches"]}
+
+    sweep, codec, cpu_baseline = None, None, None
+    if world == 1 and not args.quick:
+        # config-faithful batch and a few others, same protocol (shorter)
+        sweep = {}
+        for b in args.sweep:
+            if b == B:
+                continue
+            ks = max(3, args.steps // 2)
+            r = timed(b, ks, max(3, args.warmup))
+            sweep[f"per_gpu_batch_{b}"] = {"samples_per_s": b * ks / (r["ms_total"] * 1e-3), "ms_per_step": r["ms_per_step"],
+                                           "gpu_launches": r["launches"],
+                                           "tensor_frac_whole_step": flops_per_sample(D) * b / (r["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"]}
+            del r
+            torch.cuda.empty_cache()
+        codec = codec_bench(m, _lib, dev, pk)
+        cpu_baseline = time_cpu_reference(T, min(B, 128), 50, 1, budget_s=20.0)
+        cpu_baseline.pop("ms_per_step", None)
+
+    if rank == 0:
+        line = {
+            "metric": "imf_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, B, D, nf),
+            "e2e": e2e, "gpu_launches": main["launches"], "clocks": main["clocks"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "tensor_frac_whole_step": flops_per_sample(D) * B / (main["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"],
+            "kernel_families": families, "sweep": sweep, "codec": codec,
+            "wall_ms_per_step": main["wall_ms"] / args.steps, "loss": main["loss"],
+        }
+        print(json.dumps(line))
+    dp.destroy()
+    return 0
+
+
+def codec_bench(m, _lib, dev, pk):
+    """MDCT -> encode -> 1-NFE mean-flow sample -> IMDCT on 10 s synthetic 44.1 kHz clips (BASELINE configs[4])."""
+    import torch
+    T, N, hop, D = 441000, 512, 256, 1024
+    model = m.ConditionalFlow(D, CFG["condition_dimension"], CFG["num_blocks"], CFG["latent_dimension"])
+    params = model.init(CFG["seed"], device=dev)["params"]
+    out = {}
+    for Bc in (16, 64):
+        x = 0.1 * torch.randn(Bc, T, device=dev, generator=torch.Generator(device=dev).manual_seed(42))
+
+        def run():
+            X = m.mdct(x, N, hop)                                  # [Bc, 1721, 512]
+            nf = X.shape[1]
+            pad = (-nf) % (D // N)
+            Xp = torch.nn.functional.pad(X, (0, 0, 0, pad)) if pad else X
+            rows = Xp.reshape(-1, D)                               # [Bc*861, 1024]
+            lat = model.apply({"params": params}, rows, method="encode")
+            rec = m.sample_mean_flow(model.apply, D, params, 0, lat, nfe=1)
+            Xr = rec.reshape(Bc, -1, N)[:, :nf]
+            return m.imdct(Xr.contiguous(), N, hop)
+
+        for _ in range(2):
+            y = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 5
+        e0.record()
+        for _ in range(iters):
+            y = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[f"clips_{Bc}"] = {"audio_seconds_per_s": Bc * 10.0 / (ms * 1e-3), "ms": ms}
+    _lib.profile_enable(True)
+    x = 0.1 * torch.randn(256, T, device=dev)
+    for _ in range(3):
+        X = m.mdct(x, N, hop)
+        y = m.imdct(X, N, hop)
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    for fam in ("mdct512", "imdct512"):
+        v = prof[fam]
+        gbs = v["work"] / (v["ms"] * 1e-3) / 1e9
+        out[fam] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                    "clips": 256, "ms_per_launch": v["ms"] / v["launches"]}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mfac", choices=["mfac", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch")
+    ap.add_argument("--noise-dimension", type=int, default=784, help="raw samples per example (T)")
+    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 18944])
+    ap.add_argument("--quick", action="store_true", help="skip sweep / codec / cpu baseline")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "mfac":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_mfac(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -182,6 +182,15 @@ MFAC_API int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int
 MFAC_API int mfac_debug_set_simt_gemm(int32_t on);
 MFAC_API int mfac_debug_counters(int64_t* kernel_launches);
 
+/* ------------------------------------------------------------------ per-kernel timing (bench.py roofline)
+ * While enabled, every launch of a profiled kernel family is bracketed by CUDA events on its own
+ * stream (no synchronisation, no serialisation).  mfac_profile_collect synchronises the device and
+ * returns, per family, the number of launches, the summed event time (ms) and the summed algorithmic
+ * work (FLOPs for MFAC_PROF_GEMM, bytes for the HBM-bound families). */
+enum MfacProfFamily { MFAC_PROF_GEMM = 0, MFAC_PROF_MDCT = 1, MFAC_PROF_IMDCT = 2, MFAC_PROF_ADAMW = 3, MFAC_PROF_FAMILIES = 4 };
+MFAC_API int mfac_profile_enable(int32_t on);
+MFAC_API int mfac_profile_collect(int64_t* launches, double* ms, double* work);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ PROTOTYPES = {
     "mfac_debug_gemm_bf16": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
     "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
     "mfac_debug_counters": (C.c_int, [C.POINTER(_I64)]),
+    "mfac_profile_enable": (C.c_int, [_I32]),
+    "mfac_profile_collect": (C.c_int, [C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 WS_FORWARD, WS_LOSS_GRAD, WS_SAMPLE = 0, 1, 2
@@ -103,6 +105,21 @@ def launches() -> int:
     n = _I64(0)
     lib().mfac_debug_counters(C.byref(n))
     return int(n.value)
+
+
+PROF_FAMILIES = ("gemm_tcgen05", "mdct512", "imdct512", "adamw")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().mfac_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_collect() -> dict:
+    """{family: {"launches", "ms", "work"}}; synchronises the device."""
+    n = len(PROF_FAMILIES)
+    launches, ms, work = (_I64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+    check(lib().mfac_profile_collect(launches, ms, work), "profile_collect")
+    return {f: {"launches": int(launches[i]), "ms": float(ms[i]), "work": float(work[i])} for i, f in enumerate(PROF_FAMILIES)}
 
 
 def require_cuda(t, name: str = "input"):

@@ -12,6 +12,8 @@
 
 namespace mfac {
 void count_launch();
+void* profile_begin(int family, double work, cudaStream_t s);
+void profile_end(void* token, cudaStream_t s);
 
 namespace {
 
@@ -147,7 +149,10 @@ int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, 
   a.inv_bc1 = (float)(1.0 / (1.0 - std::pow((double)b1, c)));
   a.inv_bc2 = (float)(1.0 / (1.0 - std::pow((double)b2, c)));
   const int64_t threads = mfac::ceil_div<int64_t>(d.total, 4);
+  // 16 B read + 12 B write per parameter, + 2 B bf16 shadow
+  void* prof = mfac::profile_begin(MFAC_PROF_ADAMW, (shadow ? 30.0 : 28.0) * (double)d.total, (cudaStream_t)stream);
   mfac::adamw_kernel<<<(unsigned)mfac::ceil_div<int64_t>(threads, 256), 256, 0, (cudaStream_t)stream>>>(a, d);
+  mfac::profile_end(prof, (cudaStream_t)stream);
   mfac::count_launch();
   return mfac::launch_status();
 }

@@ -235,6 +235,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t out
                    int box_outer);
 bool simt_gemm_enabled();
 void count_launch();
+void* profile_begin(int family, double work, cudaStream_t s);
+void profile_end(void* token, cudaStream_t s);
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
@@ -260,7 +262,9 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmShape shape{M, N, K};
+  void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
+  profile_end(prof, stream);
   count_launch();
   return launch_status();
 }

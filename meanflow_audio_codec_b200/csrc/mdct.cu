@@ -25,6 +25,8 @@
 namespace mfac {
 
 void count_launch();
+void* profile_begin(int family, double work, cudaStream_t s);
+void profile_end(void* token, cudaStream_t s);
 
 struct StridedIO {
   int64_t in_clip_stride, in_elem_stride;    // MDCT: x ; IMDCT: X (elem stride = frame stride)
@@ -436,7 +438,9 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
       configured = true;
     }
     dim3 grid((unsigned)ceil_div<int64_t>(nf, fpc), (unsigned)B);
+    void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)B * ((double)T + (double)nf * N), stream);
     mdct512_kernel<<<grid, MDCT_WARPS * 32, smem, stream>>>(x, X, ts.fft, io, T, nf, hop, fpc, (int)seg_len);
+    profile_end(prof, stream);
     count_launch();
     return launch_status();
   }
@@ -476,7 +480,9 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
       configured = true;
     }
     dim3 grid((unsigned)ceil_div<int64_t>(L, spc), (unsigned)B);
+    void* prof = profile_begin(MFAC_PROF_IMDCT, 4.0 * (double)B * ((double)L + (double)nf * N), stream);
     imdct512_kernel<<<grid, MDCT_WARPS * 32, smem, stream>>>(X, y, ts.fft, io, nf, L, hop, (int)spc, max_frames);
+    profile_end(prof, stream);
     count_launch();
     return launch_status();
   }

@@ -3,6 +3,7 @@
 // launch counters and the GEMM test hook.
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 
@@ -30,6 +31,34 @@ void resolve_encode() {
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-launch event timing -------------------------------------------------
+namespace {
+struct ProfRecord {
+  int family;
+  double work;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRecord> g_prof;
+std::atomic<int> g_prof_on{0};
+}  // namespace
+
+bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+void* profile_begin(int family, double work, cudaStream_t s) {
+  if (!profile_enabled()) return nullptr;
+  ProfRecord r{family, work, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return nullptr;
+  cudaEventRecord(r.e0, s);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back(r);
+  return reinterpret_cast<void*>(g_prof.size());  // 1-based index
+}
+void profile_end(void* token, cudaStream_t s) {
+  if (!token) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  cudaEventRecord(g_prof[reinterpret_cast<size_t>(token) - 1].e1, s);
+}
 bool simt_gemm_enabled() { return g_simt.load(std::memory_order_relaxed) != 0; }
 
 int num_sms() {
@@ -95,6 +124,31 @@ int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int64_t M, i
 
 int mfac_debug_set_simt_gemm(int32_t on) {
   mfac::g_simt.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+int mfac_profile_enable(int32_t on) {
+  mfac::g_prof_on.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+int mfac_profile_collect(int64_t* launches, double* ms, double* work) {
+  using namespace mfac;
+  if (!launches || !ms || !work) return MFAC_ERR_NULL;
+  MFAC_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (int f = 0; f < MFAC_PROF_FAMILIES; ++f) { launches[f] = 0; ms[f] = 0.0; work[f] = 0.0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.family >= 0 && r.family < MFAC_PROF_FAMILIES) {
+      launches[r.family] += 1;
+      ms[r.family] += t;
+      work[r.family] += r.work;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
   return MFAC_SUCCESS;
 }
 

@@ -1,0 +1,126 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/mfac.h declares, and its host-only
+entry points and the Python mirrors' argument checking work without a GPU (no compute calls here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import meanflow_audio_codec_b200 as m
+from meanflow_audio_codec_b200 import _lib
+from oracle import imf_np, mdct_np
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "mfac.h").read_text()
+    return sorted(set(re.findall(r"MFAC_API[^;(]*?\b(mfac_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mfac.h but not exported by libmfac.so"
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header drifted apart"
+
+
+def test_version_and_status_strings(lib):
+    assert lib.mfac_version() >= 100
+    assert lib.mfac_status_string(0) == b"success"
+    assert b"workspace" in lib.mfac_status_string(-3)
+    assert lib.mfac_status_string(-1002) != b"unknown status"  # CUDA error passthrough
+
+
+@pytest.mark.parametrize("T,N,hop", [(784, 512, 256), (100, 512, 256), (441000, 512, 256), (1024, 256, 128), (3000, 576, 288)])
+def test_frame_arithmetic_matches_reference_rule(lib, T, N, hop):
+    nf = lib.mfac_mdct_num_frames(T, N, hop)
+    assert nf == mdct_np.num_frames(T, N, hop) == m.mdct.__globals__["num_frames"](T, N, hop)
+    assert lib.mfac_imdct_length(nf, N, hop) == mdct_np.padded_length(nf, N, hop)
+    assert lib.mfac_mdct_num_frames(0, N, hop) < 0 and lib.mfac_imdct_length(1, 0, hop) < 0
+
+
+@pytest.mark.parametrize("D,L,Cd,nb", [(1024, 256, 128, 8), (8, 64, 32, 2), (6, 64, 32, 2), (3584, 256, 128, 8)])
+def test_param_layout_matches_flax_tree_order(lib, D, L, Cd, nb):
+    dims = _lib.MlpDims(D, L, Cd, nb)
+    shapes = imf_np.param_shapes(D, L, Cd, nb)
+    total = sum(int(np.prod(s)) for _, s in shapes)
+    assert lib.mfac_mlp_param_count(C.byref(dims)) == total
+    model = m.ConditionalFlow(D, Cd, nb, L)
+    assert model.param_count() == total
+    off = 0
+    sl = model.leaf_slices()
+    for i, (name, shp) in enumerate(shapes):
+        path = tuple(name.split("/"))
+        assert sl[path] == (off, shp)
+        block = -1 if path[0] == "encoder" else int(path[0].split("_")[1])
+        which = i % 8 if block >= 0 else i - 8 * nb
+        o, r, c = C.c_int64(), C.c_int64(), C.c_int64()
+        assert lib.mfac_mlp_param_offset(C.byref(dims), block, which, C.byref(o), C.byref(r), C.byref(c)) == 0
+        assert o.value == off and r.value * c.value == int(np.prod(shp))
+        off += int(np.prod(shp))
+    assert lib.mfac_workspace_bytes(_lib.WS_LOSS_GRAD, C.byref(dims), 128) > lib.mfac_workspace_bytes(_lib.WS_FORWARD, C.byref(dims), 128) > 0
+    assert lib.mfac_mlp_shadow_bytes(C.byref(dims)) >= 2 * (total - (sum(int(np.prod(s)) for n, s in shapes if n.endswith("bias"))))
+
+
+def test_bad_dims_are_rejected(lib):
+    bad = _lib.MlpDims(8, 64, 31, 2)  # odd condition dimension
+    assert lib.mfac_mlp_param_count(C.byref(bad)) < 0
+    assert lib.mfac_workspace_bytes(0, C.byref(bad), 4) == 0
+    with pytest.raises(ValueError):
+        m.ConditionalFlow(8, 31, 2, 64)
+
+
+def test_python_mirror_raises_like_the_reference_before_any_compute():
+    with pytest.raises(TypeError):          # mdct.py:189-190
+        m.mdct(np.zeros(100), 512)
+    with pytest.raises(ValueError):         # mdct.py:191-192
+        m.mdct(torch.zeros(()), 512)
+    with pytest.raises(ValueError):         # mdct.py:460-461
+        m.mdct(torch.zeros(100), 0)
+    with pytest.raises(ValueError):         # mdct.py:462-463
+        m.mdct(torch.zeros(100), 512, -3)
+    with pytest.raises(ValueError):         # mdct.py:249-250
+        m.imdct(torch.zeros(512), 512)
+    with pytest.raises(TypeError):
+        m.imdct([[0.0] * 512], 512)
+    with pytest.raises(ValueError):
+        m.MDCTConfig(window_size=-1)
+    cfg = m.MDCTConfig(window_size=512)
+    assert cfg.hop_size == 256              # mdct.py:77-78
+    tok = m.MDCTTokenization(config=cfg)
+    with pytest.raises(ValueError):         # tokenization.py:94
+        tok.tokenize(torch.zeros(2, 3, 4, 5))
+    with pytest.raises(ValueError):         # tokenization.py:105-106
+        tok.detokenize(torch.zeros(2, 512))
+    assert m.compute_token_shape(tok, 784, "mnist") == (2, 512)
+    assert m.compute_tokenized_dimension(tok, 784, "mnist") == 1024
+    assert m.compute_token_shape(tok, 441000, "audio") == (1721, 512)
+    with pytest.raises(ValueError):
+        m.compute_token_shape(tok, 784, "imagenet")
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors (no oracle / torch fallback)."""
+    with pytest.raises(m.MfacError):
+        m.mdct(torch.zeros(2, 1000), 512)
+    with pytest.raises(m.MfacError):
+        m.imdct(torch.zeros(2, 3, 512), 512)
+    src = "".join(p.read_text() for p in (ROOT / "meanflow_audio_codec_b200").glob("*.py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_tokenization_factory_from_reference_config():
+    class Cfg:
+        tokenization_strategy = "mdct"
+        tokenization_config = {"window_size": 512, "hop_size": 256}
+    tok = m.create_tokenization_strategy(Cfg)
+    assert (tok.config.window_size, tok.config.hop_size) == (512, 256)
+    Cfg.tokenization_strategy = None
+    assert m.create_tokenization_strategy(Cfg) is None
+    Cfg.tokenization_strategy = "wavelet"
+    with pytest.raises(ValueError):
+        m.create_tokenization_strategy(Cfg)
