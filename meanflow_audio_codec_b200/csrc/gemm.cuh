@@ -7,8 +7,13 @@
 //                                 128B-swizzled shared-memory stages (mbarrier full/empty)
 //   warp 1      MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16);
 //                                 tcgen05.commit releases smem stages and publishes the tile
-//   warps 2..5  epilogue       -- tcgen05.ld the fp32 accumulator (thread == tile row),
-//                                 apply the fused epilogue functor, write global memory
+//   warps 2..9  epilogue       -- tcgen05.ld the fp32 accumulator (thread == tile row),
+//                                 apply the fused epilogue functor, write global memory.
+//                                 Two warps per TMEM lane quarter alternate 32-column chunks; each chunk is
+//                                 transposed through shared memory so the functor sees row-contiguous
+//                                 float4 fragments and all its global traffic is fully coalesced.
+// Optional split-K (weight gradients: M,N small, K = batch): work items are (tile, k-slice) pairs
+// and the epilogue accumulates with red.global.add into a zero-initialised output.
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
 //
@@ -23,13 +28,16 @@
 // rows < M and 32-column groups that start below N (N must be a multiple of 32).
 #pragma once
 
+#include <cmath>
+
 #include "mfac_common.cuh"
 
 namespace mfac {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SMEM_BUDGET = 196608;  // bytes of operand stages
 
 template <int BN>
@@ -39,13 +47,23 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // per-warp 32x32 fp32 transpose buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
 };
 
+// Epilogue contract.  The accumulator arrives thread-per-row (tcgen05.ld 32x32b: lane == tile row); a direct
+// global access in that layout touches 16-byte pieces of 32 different rows per instruction (partial sectors,
+// 2-3 TB/s at best).  Each epilogue warp therefore transposes its 32x32 fp32 chunk through a private, XOR-swizzled
+// 4 KB shared-memory buffer and hands the functor row-contiguous fragments:
+//     epi.load(row, col, regs)            global reads of the fragment (issued one chunk ahead of use)
+//     epi.frag(row, col, float4 acc, regs) row < M, col % 4 == 0, 8 consecutive lanes cover 32 columns of one row
+// so every global load/store the functor issues is a full 32-byte sector (bf16) or 128-byte line (fp32).
 struct GemmShape {
   int M, N, K;
+  int splits;        // split-K factor (1 = none); work item = tile * splits + split
+  int kb_per_split;  // 64-wide k-blocks per split
 };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -59,7 +77,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -71,7 +90,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_tiles = ceil_div(shape.M, GEMM_BM);
   const int n_tiles = ceil_div(shape.N, BN);
   const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = ceil_div(shape.K, GEMM_BK);
+  const int k_blocks_total = ceil_div(shape.K, GEMM_BK);
+  const int num_items = num_tiles * shape.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -82,7 +102,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -99,10 +119,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t kit = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item / shape.splits, sp = item % shape.splits;
         const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++kit) {
+        const int kb0 = sp * shape.kb_per_split;
+        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -130,13 +153,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
       uint32_t kit = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int sp = item % shape.splits;
+        const int kb0 = sp * shape.kb_per_split;
+        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
         const uint32_t as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++kit) {
+        for (int kb = kb0; kb < kb1; ++kb, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -151,7 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      : umma_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = B_MN ? umma_smem_desc_sw128(b_addr + kk * 2048, 8192, 1024)
                                      : umma_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs retire
         }
@@ -159,25 +185,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which of the quarter's two warps: even / odd chunks
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int tile = item / shape.splits;
       const uint32_t as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;
+      float4* st = reinterpret_cast<float4*>(sStage + (warp - 2) * 4096);  // [32 rows][8 x 16 B], piece ^= row & 7
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
+      const int fr = lane >> 3, fp = lane & 7;  // fragment i of this lane: row row0 + 4 i + fr, columns col0 + 4 fp ..
+      // Global operands of a chunk's 8 fragments are fetched (coalesced) one chunk ahead: the first chunk's
+      // while this tile's MMAs are still running, the next one's while the current chunk is written out.
+      typename Epi::Regs regs[8];
+      if (n0 + half * 32 < shape.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, n0 + half * 32 + 4 * fp, regs[i]);
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= shape.N) break;  // warp-uniform
         float acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < shape.M && col0 < shape.N) epi(row, col0, acc);
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          st[lane * 8 + (p ^ (lane & 7))] = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + fr;
+          const float4 u = st[r * 8 + (fp ^ (r & 7))];
+          if (row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, regs[i]);
+        }
+        if (c + 2 < BN / 32 && col0 + 64 < shape.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, col0 + 64 + 4 * fp, regs[i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -218,7 +272,12 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmShape shape, 
       acc[j] = fmaf(a, b, acc[j]);
     }
   }
-  epi(row, col0, acc);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    typename Epi::Regs regs;
+    epi.load(row, col0 + j, regs);
+    epi.frag(row, col0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), regs);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -235,12 +294,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t out
                    int box_outer);
 bool simt_gemm_enabled();
 void count_launch();
-void* profile_begin(int family, double work, cudaStream_t s);
+void* profile_begin(int family, double work, cudaStream_t s, const char* label = nullptr, int M = 0, int N = 0, int K = 0);
 void profile_end(void* token, cudaStream_t s);
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int splits) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tmA, tmB;
   if (A_MN) {
@@ -260,9 +319,15 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
     configured = true;
   }
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  GemmShape shape{M, N, K};
-  void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
+  const int k_blocks = ceil_div(K, GEMM_BK);
+  if (splits > k_blocks) splits = k_blocks;
+  if (splits < 1) splits = 1;
+  const int kbps = ceil_div(k_blocks, splits);
+  splits = ceil_div(k_blocks, kbps);  // no empty slice
+  const int items = tiles * splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  GemmShape shape{M, N, K, splits, kbps};
+  void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
   profile_end(prof, stream);
   count_launch();
@@ -271,9 +336,11 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
 
 // C = A * B with the given epilogue.  N must be a multiple of 32; K and M are arbitrary
 // (TMA zero-fills), leading dimensions must be multiples of 8 elements (16-byte TMA strides).
+// split_k = true lets the launcher slice K so that (tiles x slices) covers the machine; the epilogue
+// must then accumulate atomically (Epi::kAtomic) into a zero-initialised output.
 template <bool A_MN, bool B_MN, class Epi>
 int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
-                cudaStream_t stream, int force_bn = 0) {
+                cudaStream_t stream, int force_bn = 0, bool split_k = false) {
   if (M <= 0 || N <= 0 || K <= 0) return MFAC_ERR_BAD_SHAPE;
   if (N % 32 != 0 || A.ld % 8 != 0 || B.ld % 8 != 0) return MFAC_ERR_UNSUPPORTED;
   if (A.mn_major != A_MN || B.mn_major != B_MN) return MFAC_ERR_UNSUPPORTED;
@@ -281,7 +348,7 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
     SimtOperand a{reinterpret_cast<const __nv_bfloat16*>(A.ptr), A.ld, A_MN ? 1 : 0};
     SimtOperand b{reinterpret_cast<const __nv_bfloat16*>(B.ptr), B.ld, B_MN ? 1 : 0};
     const int64_t threads = (int64_t)M * (N / 32);
-    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K}, epi);
+    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K, 1, 0}, epi);
     count_launch();
     return launch_status();
   }
@@ -293,16 +360,35 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
     const int tiles256 = ceil_div(M, GEMM_BM) * ceil_div(N, 256);
     bn = (N % 256 == 0 && tiles256 >= num_sms()) ? 256 : 128;
   }
-  if (bn == 256) return launch_gemm_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream);
-  return launch_gemm_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream);
+  int splits = 1;
+  if (split_k) {
+    // Weight gradients: few output tiles, K = batch.  Pick the slice count whose (tiles x slices) work
+    // items fill whole waves of the machine best, with at least 4 k-blocks per item.
+    bn = force_bn ? force_bn : 128;
+    const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
+    const int k_blocks = ceil_div(K, GEMM_BK);
+    double best = -1.0;
+    for (int sp = 1; sp <= 32 && sp <= k_blocks; ++sp) {
+      if (sp > 1 && k_blocks / sp < 4) break;
+      const int items = tiles * ceil_div(k_blocks, ceil_div(k_blocks, sp));
+      const double waves = (double)items / num_sms();
+      const double eff = waves / std::ceil(waves) - 0.004 * sp;  // mild preference for fewer atomics
+      if (eff > best) { best = eff; splits = sp; }
+    }
+  }
+  if (bn == 256) return launch_gemm_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);
+  return launch_gemm_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);
 }
 
 // Plain epilogue used by the test hook and the weight-gradient GEMMs.
 struct EpiStoreF32 {
+  static constexpr const char* name = "store_f32";
+  struct Regs {};
   float* C;
   int64_t ldc;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    store_f32x32(C + (int64_t)row * ldc + col0, acc);
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&) const {
+    *reinterpret_cast<float4*>(C + (int64_t)row * ldc + col) = acc;
   }
 };
 

@@ -42,7 +42,14 @@ int gemm_dx(const __nv_bfloat16* G, int ldg, const __nv_bfloat16* W, int M, int 
 template <class Epi>
 int gemm_dw(const __nv_bfloat16* Act, int lda, const __nv_bfloat16* G, int ldg, int M, int N, int Bk, const Epi& epi,
             cudaStream_t s) {
-  return launch_gemm<true, true>(GemmOperandDesc{Act, lda, true}, GemmOperandDesc{G, ldg, true}, M, N, Bk, epi, s);
+  return launch_gemm<true, true>(GemmOperandDesc{Act, lda, true}, GemmOperandDesc{G, ldg, true}, M, N, Bk, epi, s, 0,
+                                 /*split_k=*/true);
+}
+
+// NV of the vectorised row kernels, or 0 when the geometry needs the generic (padded) kernels.
+inline int vec_rows(const Dims& d) {
+  if (d.D != d.Dp || d.L != d.Lp || d.Ip % 256 != 0 || d.Ip > 2048) return 0;
+  return d.Ip / 256;
 }
 
 int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
@@ -56,8 +63,34 @@ int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream
     MFAC_CUDA_OK(cudaFuncSetAttribute(imf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  if (tangent) lnmod_kernel<true><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
-  else lnmod_kernel<false><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
+  const int nv = vec_rows(d);
+  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8);
+#define MFAC_LNMOD_CASE(NVV)                                                              \
+  case NVV:                                                                               \
+    if (tangent) lnmod_vec_kernel<NVV, true><<<vgrid, 256, 0, s>>>(a, d, B);              \
+    else lnmod_vec_kernel<NVV, false><<<vgrid, 256, 0, s>>>(a, d, B);                     \
+    break;
+  switch (nv) {
+    MFAC_LNMOD_CASE(1) MFAC_LNMOD_CASE(2) MFAC_LNMOD_CASE(3) MFAC_LNMOD_CASE(4)
+    MFAC_LNMOD_CASE(5) MFAC_LNMOD_CASE(6) MFAC_LNMOD_CASE(7) MFAC_LNMOD_CASE(8)
+    default:
+      if (tangent) lnmod_kernel<true><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
+      else lnmod_kernel<false><<<(unsigned)B, ROW_THREADS, smem, s>>>(a, d);
+  }
+#undef MFAC_LNMOD_CASE
+  count_launch();
+  return launch_status();
+}
+
+int ln_bwd(const LnBwdArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
+  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8);
+#define MFAC_LNBWD_CASE(NVV) case NVV: ln_bwd_vec_kernel<NVV><<<vgrid, 256, 0, s>>>(a, d, B); break;
+  switch (vec_rows(d)) {
+    MFAC_LNBWD_CASE(1) MFAC_LNBWD_CASE(2) MFAC_LNBWD_CASE(3) MFAC_LNBWD_CASE(4)
+    MFAC_LNBWD_CASE(5) MFAC_LNBWD_CASE(6) MFAC_LNBWD_CASE(7) MFAC_LNBWD_CASE(8)
+    default: ln_bwd_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Ip * 8, s>>>(a, d);
+  }
+#undef MFAC_LNBWD_CASE
   count_launch();
   return launch_status();
 }
@@ -102,8 +135,8 @@ int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_
 
 int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* partial, float* out, int kind, int limit, const Dims& d,
            cudaStream_t s) {
-  const int R = (int)ceil_div<int64_t>(B, COLSUM_ROWS);
-  colsum_partial_kernel<<<dim3(ld / 64, R), 256, 0, s>>>(G, ld, B, partial);
+  const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
+  colsum_partial_vec_kernel<<<dim3(ceil_div(ld, 256), R), 256, 0, s>>>(G, ld, B, partial);
   count_launch();
   colsum_final_kernel<<<blocks_for(ld, 128), 128, 0, s>>>(partial, ld, R, out, kind, limit, d);
   count_launch();
@@ -172,7 +205,7 @@ struct LossGradPlan {
     g_x = ar.take<float>(B * d.Dp);
     g_lat = ar.take<float>(B * d.Lp);
     g_hin = ar.take<float>(B * d.Ip);
-    partial = ar.take<float>(ceil_div<int64_t>(B, COLSUM_ROWS) * d.Mp);
+    partial = ar.take<float>(ceil_div<int64_t>(B, COLSUM_VROWS) * d.Mp);
     g_o = ar.take<__nv_bfloat16>(B * d.Dp);
     g_a = ar.take<__nv_bfloat16>(B * d.Ip);
     g_m = ar.take<__nv_bfloat16>(B * d.Mp);
@@ -340,38 +373,38 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   count_launch();
   sum_rows_kernel<<<1, 1024, 0, s>>>(p.row_loss, B, loss);
   count_launch();
-  // ---- backward through the primal u rows
+  // ---- backward through the primal u rows (weight gradients accumulate split-K partials atomically)
+  MFAC_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)d.total * 4, s));
   MFAC_CUDA_OK(cudaMemsetAsync(p.g_lat, 0, (size_t)B * d.Lp * 4, s));
   for (int k = d.nb - 1; k >= 0; --k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     SavedBlock& sb = p.blk[k];
     float* gk = grads + (int64_t)k * d.blk_stride;
     const float* x_in = p.xs + (int64_t)k * B * d.Dp;
-    bwd_block_out_kernel<<<blocks_for(B * d.Dp, 256), 256, 0, s>>>(p.g_x, sb.m, sb.o, p.g_o, p.g_m, d, B);
+    bwd_block_out_vec_kernel<<<blocks_for(B * d.Dp / 8, 256), 256, 0, s>>>(p.g_x, sb.m, sb.o, p.g_o, p.g_m, d, B);
     count_launch();
-    MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, d}, s));
+    MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
     MFAC_OK(colsum(p.g_o, d.Dp, B, p.partial, gk + d.o_m2b, MAP_ID, d.D, d, s));
     MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
-    MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, d}, s));
+    MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
     MFAC_OK(colsum(p.g_a, d.Ip, B, p.partial, gk + d.o_m1b, MAP_CM, 0, d, s));
     MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearF32{nullptr, p.g_hin, d.Ip}, s));
     LnBwdArgs lb{p.g_hin, p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
-    ln_bwd_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Ip * 8, s>>>(lb, d);
-    count_launch();
+    MFAC_OK(ln_bwd(lb, d, B, s));
     MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
-                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, d}, s));
+                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
     MFAC_OK(colsum(p.g_m, d.Mp, B, p.partial, gk + d.o_c2b, MAP_MM, 0, d, s));
     MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
-    MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, d}, s));
+    MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, 1, d}, s));
     MFAC_OK(colsum(p.g_ac, d.Cp, B, p.partial, gk + d.o_c1b, MAP_ID, d.C, d, s));
   }
   // ---- encoder backward
   f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);
   count_launch();
-  MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, d}, s));
+  MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, 1, d}, s));
   MFAC_OK(colsum(p.g_latb, d.Lp, B, p.partial, grads + d.o_e2b, MAP_ID, d.L, d, s));
   MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, s));
-  MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, d}, s));
+  MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, 1, d}, s));
   MFAC_OK(colsum(p.g_ae, d.Hep, B, p.partial, grads + d.o_e1b, MAP_ID, d.He, d, s));
   // ---- optional intermediates for parity tests
   if (aux) {

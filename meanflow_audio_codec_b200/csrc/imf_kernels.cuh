@@ -431,94 +431,303 @@ __global__ void fill_normal_kernel(float* out, int Dp, int D, int64_t B, uint64_
 }
 
 // ---------------------------------------------------------------------------------------
-// fused GEMM epilogues: operator()(row, col0, acc[32]) with thread == output row
+// Vectorised fast paths of the row kernels: one warp per row, the whole row in registers, 16/32-byte
+// accesses.  Preconditions (checked by the host): D == Dp, L == Lp (no padded columns) and
+// Ip == 256 * NV with NV <= 8.  Lane l owns the 8-column vectors v = l + 32 i, i < NV.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8_f32(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8_f32(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <int NV, bool TANGENT>
+__global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float c[NV][8], cd[TANGENT ? NV : 1][8];
+  float sum = 0.f, sq = 0.f, sumd = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = 8 * (lane + 32 * i);
+    if (col < d.Lp) {
+      if (a.lat) ld8_f32(a.lat + b * d.Lp + col, c[i]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c[i][q] = 0.f;
+      }
+      if (TANGENT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cd[i][q] = 0.f;
+      }
+    } else {
+      ld8_f32(a.x + b * d.Dp + (col - d.Lp), c[i]);
+      if (TANGENT) ld8_f32(a.xd + b * d.Dp + (col - d.Lp), cd[i]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sum += c[i][q];
+      sq += c[i][q] * c[i][q];
+      if (TANGENT) sumd += cd[i][q];
+    }
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float mu = warp_sum(sum) * inv_i;
+  const float rstd = rsqrtf(fmaxf(0.f, warp_sum(sq) * inv_i - mu * mu) + LN_EPS);
+  float mean_cd = 0.f, mean_ncd = 0.f;
+  if (TANGENT) {
+    mean_cd = warp_sum(sumd) * inv_i;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += (c[i][q] - mu) * rstd * cd[i][q];
+    mean_ncd = warp_sum(acc) * inv_i;
+  }
+  if (lane == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
+  const __nv_bfloat16* mrow = a.m + b * d.Mp;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = 8 * (lane + 32 * i);
+    float s1[8], sh[8], h[8], n[8];
+    ld8_bf16(mrow + col, s1);
+    ld8_bf16(mrow + d.Ip + col, sh);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      n[q] = (c[i][q] - mu) * rstd;
+      h[q] = (1.0f + s1[q]) * n[q] + sh[q];
+    }
+    st8_bf16(a.hin + b * d.Ip + col, h);
+    if (TANGENT) {
+      float s1d[8], shd[8];
+      ld8_bf16(a.md + b * d.Mp + col, s1d);
+      ld8_bf16(a.md + b * d.Mp + d.Ip + col, shd);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float nd = (cd[i][q] - mean_cd - n[q] * mean_ncd) * rstd;
+        h[q] = s1d[q] * n[q] + (1.0f + s1[q]) * nd + shd[q];
+      }
+      st8_bf16(a.hind + b * d.Ip + col, h);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float mu = a.mu[b], rstd = a.rstd[b];
+  float n[NV][8], gn[NV][8];
+  float s1sum = 0.f, s2sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = 8 * (lane + 32 * i);
+    float c[8], gh[8], s1[8], gs1[8];
+    if (col < d.Lp) ld8_f32(a.lat + b * d.Lp + col, c);
+    else ld8_f32(a.x + b * d.Dp + (col - d.Lp), c);
+    ld8_f32(a.g_hin + b * d.Ip + col, gh);
+    ld8_bf16(a.m + b * d.Mp + col, s1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      n[i][q] = (c[q] - mu) * rstd;
+      gn[i][q] = gh[q] * (1.0f + s1[q]);
+      gs1[q] = gh[q] * n[i][q];
+      s1sum += gn[i][q];
+      s2sum += gn[i][q] * n[i][q];
+    }
+    st8_bf16(a.g_m + b * d.Mp + col, gs1);
+    st8_bf16(a.g_m + b * d.Mp + d.Ip + col, gh);
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float m1 = warp_sum(s1sum) * inv_i, m2 = warp_sum(s2sum) * inv_i;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = 8 * (lane + 32 * i);
+    float* dst = col < d.Lp ? a.g_lat + b * d.Lp + col : a.g_x + b * d.Dp + (col - d.Lp);
+    float acc[8];
+    ld8_f32(dst, acc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += (gn[i][q] - m1 - n[i][q] * m2) * rstd;
+    st8_f32(dst, acc);
+  }
+}
+
+// 8 elements per thread; Dp is a multiple of 64 so a vector never straddles a row
+__global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o,
+                                                                __nv_bfloat16* g_o, __nv_bfloat16* g_m, Dims d, int64_t B) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= B * d.Dp) return;
+  const int64_t b = i / d.Dp;
+  const int j = (int)(i % d.Dp);
+  const float inv_nb = 1.0f / (float)d.nb;
+  float g[8], s2[8], ov[8], go[8], gs2[8];
+  ld8_f32(g_x + i, g);
+  ld8_bf16(m + b * d.Mp + 2 * d.Ip + j, s2);
+  ld8_bf16(o + i, ov);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    go[q] = g[q] * (1.0f + s2[q]) * inv_nb;
+    gs2[q] = g[q] * ov[q] * inv_nb;
+  }
+  st8_bf16(g_o + i, go);
+  st8_bf16(g_m + b * d.Mp + 2 * d.Ip + j, gs2);
+}
+
+// Column sums, stage 1, vectorised: grid (ceil(ld/256), R); thread = 8 columns x every 8th row of a 256-row slab.
+constexpr int COLSUM_VROWS = 256;
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* partial) {
+  __shared__ float s_red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_VROWS;
+  const int64_t r1 = min(B, r0 + COLSUM_VROWS);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < ld) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float v[8];
+      ld8_bf16(G + r * ld + col, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += v[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s_red[rl][cg * 8 + q] = acc[q];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < ld) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_red[q][c];
+    partial[(int64_t)blockIdx.y * ld + blockIdx.x * 256 + c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fused GEMM epilogues: frag(row, col, acc) handles 4 consecutive columns of one output row; 8 adjacent
+// lanes cover 32 columns of the same row, so every access below is sector/line coalesced (see gemm.cuh).
+// Read-only operands go through ld.global.nc so the 8 unrolled fragments' loads are issued back to back.
+// GELU uses tanh.approx.f32 (one MUFU op): its 2^-11 relative error is far inside the bf16 rounding of
+// the values it feeds.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_fast(float a) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * a * (1.0f + tanh_fast(k0 * (a + k1 * a * a * a)));
+}
+__device__ __forceinline__ float dgelu_fast(float a) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float th = tanh_fast(k0 * (a + k1 * a * a * a));
+  return 0.5f * (1.0f + th) + 0.5f * a * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * a * a);
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg_bf4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
 // g = gelu(acc + bias); optionally keeps the pre-activation a (bf16) for the tangent/backward.
 struct EpiBiasGelu {
+  static constexpr const char* name = "bias_gelu";
   const float* bias;        // padded fp32 [N]
   __nv_bfloat16* g;         // [M, ld]
   __nv_bfloat16* a_out;     // [M, ld] or null
   int64_t ld;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    float bv[32];
-    load_f32x32(bias + col0, bv);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += bv[j];
-    if (a_out) store_bf16x32(a_out + (int64_t)row * ld + col0, acc);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = gelu_tanh(acc[j]);
-    store_bf16x32(g + (int64_t)row * ld + col0, acc);
+  struct Regs { float4 b; };
+  __device__ __forceinline__ void load(int, int col, Regs& r) const { r.b = ldg_f4(bias + col); }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    acc = add4(acc, r.b);
+    const int64_t at = (int64_t)row * ld + col;
+    if (a_out) st_bf4(a_out + at, acc);
+    st_bf4(g + at, make_float4(gelu_fast(acc.x), gelu_fast(acc.y), gelu_fast(acc.z), gelu_fast(acc.w)));
   }
 };
 // out = acc * gelu'(a)   (tangent through GELU, and the backward of GELU)
 struct EpiMulDgelu {
+  static constexpr const char* name = "mul_dgelu";
   const __nv_bfloat16* a;   // [M, ld]
   __nv_bfloat16* out;       // [M, ld]
   int64_t ld;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    float av[32];
-    load_bf16x32(a + (int64_t)row * ld + col0, av);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= dgelu_tanh(av[j]);
-    store_bf16x32(out + (int64_t)row * ld + col0, acc);
+  struct Regs { float4 av; };
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const { r.av = ldg_bf4(a + (int64_t)row * ld + col); }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    const int64_t at = (int64_t)row * ld + col;
+    const float4 av = r.av;
+    st_bf4(out + at, make_float4(acc.x * dgelu_fast(av.x), acc.y * dgelu_fast(av.y), acc.z * dgelu_fast(av.z),
+                                 acc.w * dgelu_fast(av.w)));
   }
 };
 // out = acc (+ bias)
 struct EpiLinearBf16 {
+  static constexpr const char* name = "linear_bf16";
   const float* bias;  // or null
   __nv_bfloat16* out;
   int64_t ld;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    if (bias) {
-      float bv[32];
-      load_f32x32(bias + col0, bv);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += bv[j];
-    }
-    store_bf16x32(out + (int64_t)row * ld + col0, acc);
+  struct Regs { float4 b; };
+  __device__ __forceinline__ void load(int, int col, Regs& r) const { r.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    st_bf4(out + (int64_t)row * ld + col, add4(acc, r.b));
   }
 };
 struct EpiLinearF32 {
+  static constexpr const char* name = "linear_f32";
   const float* bias;  // or null
   float* out;
   int64_t ld;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    if (bias) {
-      float bv[32];
-      load_f32x32(bias + col0, bv);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += bv[j];
-    }
-    store_f32x32(out + (int64_t)row * ld + col0, acc);
+  struct Regs { float4 b; };
+  __device__ __forceinline__ void load(int, int col, Regs& r) const { r.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    st_f4(out + (int64_t)row * ld + col, add4(acc, r.b));
   }
 };
 // block output: o = acc + b2;  x_new = o (1 + s2) / nb + x_old      (mlp_flow.py:112-117)
 struct EpiBlockOut {
+  static constexpr const char* name = "block_out";
   const float* bias;          // padded [Dp]
   const __nv_bfloat16* m;     // [M, Mp]; s2 at column offset s2_off
   const float* x_old;         // [M, Dp]
-  float* x_new;               // [M, Dp] (may alias x_old)
+  float* x_new;               // [M, Dp] (may alias x_old: each element is read and written by the same thread)
   __nv_bfloat16* o_out;       // [M, Dp] or null
   int64_t ldm, ldx;
   int s2_off;
   float inv_nb;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    float t[32];
-    load_f32x32(bias + col0, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += t[j];
-    if (o_out) store_bf16x32(o_out + (int64_t)row * ldx + col0, acc);
-    load_bf16x32(m + (int64_t)row * ldm + s2_off + col0, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= (1.0f + t[j]) * inv_nb;
-    load_f32x32(x_old + (int64_t)row * ldx + col0, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += t[j];
-    store_f32x32(x_new + (int64_t)row * ldx + col0, acc);
+  struct Regs { float4 b, s2, xo; };
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const {
+    r.b = ldg_f4(bias + col);
+    r.s2 = ldg_bf4(m + (int64_t)row * ldm + s2_off + col);
+    r.xo = ldg_f4(x_old + (int64_t)row * ldx + col);
+  }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    const int64_t at = (int64_t)row * ldx + col;
+    const float4 s2 = r.s2, xo = r.xo;
+    acc = add4(acc, r.b);
+    if (o_out) st_bf4(o_out + at, acc);
+    st_f4(x_new + at, make_float4(acc.x * ((1.0f + s2.x) * inv_nb) + xo.x, acc.y * ((1.0f + s2.y) * inv_nb) + xo.y,
+                                  acc.z * ((1.0f + s2.z) * inv_nb) + xo.z, acc.w * ((1.0f + s2.w) * inv_nb) + xo.w));
   }
 };
 // tangent of the block output: xd_new = (od (1+s2) + o s2d) / nb + xd_old
 struct EpiBlockOutTangent {
+  static constexpr const char* name = "block_out_tangent";
   const __nv_bfloat16* m;     // primal modulation  [M, Mp]
   const __nv_bfloat16* md;    // tangent modulation [M, Mp]
   const __nv_bfloat16* o;     // primal o [M, Dp]
@@ -527,46 +736,52 @@ struct EpiBlockOutTangent {
   int64_t ldm, ldx;
   int s2_off;
   float inv_nb;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
-    float t[32], q[32];
-    load_bf16x32(m + (int64_t)row * ldm + s2_off + col0, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= (1.0f + t[j]);
-    load_bf16x32(md + (int64_t)row * ldm + s2_off + col0, t);
-    load_bf16x32(o + (int64_t)row * ldx + col0, q);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + q[j] * t[j]) * inv_nb;
-    load_f32x32(xd_old + (int64_t)row * ldx + col0, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += t[j];
-    store_f32x32(xd_new + (int64_t)row * ldx + col0, acc);
+  struct Regs { float4 s2, s2d, ov, xd; };
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const {
+    const int64_t at = (int64_t)row * ldx + col, am = (int64_t)row * ldm + s2_off + col;
+    r.s2 = ldg_bf4(m + am); r.s2d = ldg_bf4(md + am); r.ov = ldg_bf4(o + at); r.xd = ldg_f4(xd_old + at);
+  }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r) const {
+    const int64_t at = (int64_t)row * ldx + col;
+    const float4 s2 = r.s2, s2d = r.s2d, ov = r.ov, xd = r.xd;
+    st_f4(xd_new + at, make_float4((acc.x * (1.0f + s2.x) + ov.x * s2d.x) * inv_nb + xd.x,
+                                   (acc.y * (1.0f + s2.y) + ov.y * s2d.y) * inv_nb + xd.y,
+                                   (acc.z * (1.0f + s2.z) + ov.z * s2d.z) * inv_nb + xd.z,
+                                   (acc.w * (1.0f + s2.w) + ov.w * s2d.w) * inv_nb + xd.w));
   }
 };
-// weight gradient: padded (row, col) -> flat fp32 [rows_real, cols_real] with inverse maps
+// weight gradient: padded (row, col) -> flat fp32 [rows_real, cols_real] with inverse maps.
+// atomic = 1 under split-K: partial products are accumulated with red.global.add (output pre-zeroed).
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 struct EpiGradStore {
+  static constexpr const char* name = "grad_store";
   float* G;       // leaf base in the flat gradient
   int ld;         // real number of columns
   int row_kind, row_limit, col_kind, col_limit;
+  int atomic;
   Dims d;
-  __device__ __forceinline__ void operator()(int row, int col0, float (&acc)[32]) const {
+  struct Regs {};
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&) const {
     const int r = map_col(row_kind, row, row_limit, d);
     if (r < 0) return;
     float* dst = G + (int64_t)r * ld;
-    const int c0 = map_col(col_kind, col0, col_limit, d);
-    const int c31 = map_col(col_kind, col0 + 31, col_limit, d);
-    if (c0 >= 0 && c31 == c0 + 31) {
-      float* p = dst + c0;
-      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-        store_f32x32(p, acc);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) p[j] = acc[j];
-      }
+    const int c0 = map_col(col_kind, col, col_limit, d);
+    const int c3 = map_col(col_kind, col + 3, col_limit, d);
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (c0 >= 0 && c3 == c0 + 3 && (reinterpret_cast<uintptr_t>(dst + c0) & 15) == 0) {
+      if (atomic) red_add_v4(dst + c0, acc);
+      else st_f4(dst + c0, acc);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = map_col(col_kind, col0 + j, col_limit, d);
-        if (c >= 0) dst[c] = acc[j];
+      for (int j = 0; j < 4; ++j) {
+        const int c = map_col(col_kind, col + j, col_limit, d);
+        if (c >= 0) {
+          if (atomic) atomicAdd(dst + c, v[j]);
+          else dst[c] = v[j];
+        }
       }
     }
   }

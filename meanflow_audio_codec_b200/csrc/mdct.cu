@@ -25,7 +25,7 @@
 namespace mfac {
 
 void count_launch();
-void* profile_begin(int family, double work, cudaStream_t s);
+void* profile_begin(int family, double work, cudaStream_t s, const char* label = nullptr, int M = 0, int N = 0, int K = 0);
 void profile_end(void* token, cudaStream_t s);
 
 struct StridedIO {

@@ -2,6 +2,7 @@
 // (driver entry point resolved at run time so the library links against cudart only),
 // launch counters and the GEMM test hook.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -38,6 +39,8 @@ struct ProfRecord {
   int family;
   double work;
   cudaEvent_t e0, e1;
+  const char* label;
+  int M, N, K;
 };
 std::mutex g_prof_mu;
 std::vector<ProfRecord> g_prof;
@@ -45,9 +48,9 @@ std::atomic<int> g_prof_on{0};
 }  // namespace
 
 bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
-void* profile_begin(int family, double work, cudaStream_t s) {
+void* profile_begin(int family, double work, cudaStream_t s, const char* label, int M, int N, int K) {
   if (!profile_enabled()) return nullptr;
-  ProfRecord r{family, work, nullptr, nullptr};
+  ProfRecord r{family, work, nullptr, nullptr, label, M, N, K};
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return nullptr;
   cudaEventRecord(r.e0, s);
   std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -138,9 +141,12 @@ int mfac_profile_collect(int64_t* launches, double* ms, double* work) {
   MFAC_CUDA_OK(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lock(g_prof_mu);
   for (int f = 0; f < MFAC_PROF_FAMILIES; ++f) { launches[f] = 0; ms[f] = 0.0; work[f] = 0.0; }
+  FILE* csv = nullptr;
+  if (const char* path = getenv("MFAC_PROFILE_CSV")) csv = fopen(path, "a");  // per-launch dump for profiles/
   for (auto& r : g_prof) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.family >= 0 && r.family < MFAC_PROF_FAMILIES) {
+      if (csv) fprintf(csv, "%d,%s,%d,%d,%d,%.3f,%.6g\n", r.family, r.label ? r.label : "", r.M, r.N, r.K, t * 1e3, r.work);
       launches[r.family] += 1;
       ms[r.family] += t;
       work[r.family] += r.work;
@@ -148,6 +154,7 @@ int mfac_profile_collect(int64_t* launches, double* ms, double* work) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
+  if (csv) fclose(csv);
   g_prof.clear();
   return MFAC_SUCCESS;
 }

@@ -3,8 +3,9 @@
 Tolerances:
   * vs the fp64 oracle: <= 1e-5 relative L2 (BASELINE.json north_star; SURVEY.md R3 explains why the
     denominator is exact math and not the reference's fp32 output)
-  * vs the committed reference NumPy-baseline vectors: the reference test's own rtol=1e-4 / atol=1e-3
-    widened to atol=2e-3 (the baseline's own fp32 argument-rounding error, see tests/test_oracle_cpu.py)
+  * vs the committed reference NumPy-baseline vectors: 3e-4 relative L2 (the baseline's own fp32
+    argument-rounding error), and at the reference test's size (g1) its rtol=1e-4 with atol widened to 2e-3
+    (see tests/test_oracle_cpu.py)
   * round trip: ||imdct(mdct(x)) - (N/hop) x|| / ||(N/hop) x|| <= 1e-5 over the interior
 """
 from pathlib import Path
@@ -35,10 +36,15 @@ def test_against_reference_baseline_vectors(m, name):
     x, X, y = GOLD[name + "/x"], GOLD[name + "/X"], GOLD[name + "/y"]
     Xd = m.mdct(torch.from_numpy(x).cuda(), N, hop)
     assert tuple(Xd.shape) == X.shape
-    np.testing.assert_allclose(Xd.cpu().numpy(), X, rtol=1e-4, atol=2e-3)
     yd = m.imdct(torch.from_numpy(X).cuda(), N, hop)
     assert tuple(yd.shape) == y.shape
-    np.testing.assert_allclose(yd.cpu().numpy(), y, rtol=1e-4, atol=2e-3)
+    # the fp32 baseline is 3e-5..3e-4 (relative L2) off exact math; elementwise it is off by up to
+    # 6e-3 at N=512, so the elementwise reference tolerance is only applied at the reference test's own size (g1)
+    assert rel_l2(Xd.cpu().numpy(), X) < 3e-4
+    assert rel_l2(yd.cpu().numpy(), y) < 3e-4
+    if name == "g1":
+        np.testing.assert_allclose(Xd.cpu().numpy(), X, rtol=1e-4, atol=2e-3)
+        np.testing.assert_allclose(yd.cpu().numpy(), y, rtol=1e-4, atol=2e-3)
     # and both within 1e-5 of exact math
     assert rel_l2(Xd.cpu().numpy(), mdct_np.mdct(x, N, hop)) < 1e-5
     assert rel_l2(yd.cpu().numpy(), mdct_np.imdct(X, N, hop)) < 1e-5
