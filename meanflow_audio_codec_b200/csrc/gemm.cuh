@@ -2,12 +2,13 @@
 //
 //   C[M,N] = A[M,K] * B[K,N]      bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA per SM (grid = min(#tiles, #SMs)), 192 threads:
+// One CTA per SM (grid = min(#tiles, #SMs)), 384 threads:
 //   warp 0      TMA producer   -- cp.async.bulk.tensor tiles of A and B into a ring of
 //                                 128B-swizzled shared-memory stages (mbarrier full/empty)
 //   warp 1      MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16);
 //                                 tcgen05.commit releases smem stages and publishes the tile
-//   warps 2..9  epilogue       -- tcgen05.ld the fp32 accumulator (thread == tile row),
+//   warps 2..3  idle (complete warpgroup 0 so that it can release registers with setmaxnreg)
+//   warps 4..11 epilogue       -- tcgen05.ld the fp32 accumulator (thread == tile row),
 //                                 apply the fused epilogue functor, write global memory.
 //                                 Two warps per TMEM lane quarter alternate 32-column chunks; each chunk is
 //                                 transposed through shared memory so the functor sees row-contiguous
@@ -37,7 +38,12 @@ namespace mfac {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter, alternating 32-column chunks
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+// Warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}; warpgroups 1..2 = epilogue.  After setup warpgroup 0 gives
+// most of its registers to the epilogue warps (setmaxnreg), which keep two chunks of functor operands in flight.
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_REGS_LAUNCH = 168;  // 65536 / 384 rounded down to a multiple of 8
+constexpr int GEMM_REGS_CTRL = 56;
+constexpr int GEMM_REGS_EPI = 224;     // 128 * 40 + 256 * 232 == 384 * 168
 constexpr int GEMM_SMEM_BUDGET = 196608;  // bytes of operand stages
 
 template <int BN>
@@ -57,8 +63,10 @@ struct GemmCfg {
 // global access in that layout touches 16-byte pieces of 32 different rows per instruction (partial sectors,
 // 2-3 TB/s at best).  Each epilogue warp therefore transposes its 32x32 fp32 chunk through a private, XOR-swizzled
 // 4 KB shared-memory buffer and hands the functor row-contiguous fragments:
-//     epi.load(row, col, regs)            global reads of the fragment (issued one chunk ahead of use)
-//     epi.frag(row, col, float4 acc, regs) row < M, col % 4 == 0, 8 consecutive lanes cover 32 columns of one row
+//     epi.prefetch(m0, n0, bn, M, N, etid)      L2 prefetch of the tile's global operands, one tile ahead
+//     epi.load_col(col, cregs)                  per-column operands (bias), once per chunk
+//     epi.load(row, col, regs)                  global reads of the fragment (issued one chunk ahead of use)
+//     epi.frag(row, col, float4 acc, regs, cregs)   row < M, col % 4 == 0, 8 consecutive lanes cover 32 columns of a row
 // so every global load/store the functor issues is a full 32-byte sector (bf16) or 128-byte line (fp32).
 struct GemmShape {
   int M, N, K;
@@ -66,7 +74,90 @@ struct GemmShape {
   int kb_per_split;  // 64-wide k-blocks per split
 };
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+// One epilogue warp's share of one output tile: 32 rows (its TMEM lane quarter) x every other 32-column chunk.
+// FULL = the tile lies entirely inside the matrix (no row / column predicates in the hot loop).
+// The functor's global operands are fetched (coalesced) TWO chunks ahead into two register sets: the first two
+// chunks' while this tile's MMAs are still running, chunk j+2's as soon as chunk j has been written out.
+template <int BN, bool FULL, class Epi>
+__device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& shape, float4* st, uint32_t taddr, int row0,
+                                              int n0, int half, int lane, uint64_t* tfull, uint32_t aph) {
+  constexpr int NCH = BN / 64;              // chunks handled by this warp: c = half + 2 j
+  const int fr = lane >> 3, fp = lane & 7;  // fragment i of this lane: row row0 + 4 i + fr, columns col0 + 4 fp ..
+  if constexpr (Epi::kPrefetchDepth == 0) {
+    // store-only functors with bulky per-fragment code (gradient scatter): rolled loop, small instruction footprint
+    typename Epi::Regs nr;
+    typename Epi::ColRegs nc;
+    mbar_wait(tfull, aph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += 2) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= shape.N) break;  // warp-uniform
+      float acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        st[lane * 8 + (p ^ (lane & 7))] = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
+      __syncwarp();
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + fr;
+        const float4 u = st[r * 8 + (fp ^ (r & 7))];
+        if (row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, nr, nc);
+      }
+    }
+    return;
+  } else {
+  constexpr int DEPTH = Epi::kPrefetchDepth < NCH ? (Epi::kPrefetchDepth > 0 ? Epi::kPrefetchDepth : 1) : NCH;  // register sets in flight
+  typename Epi::Regs regs[DEPTH][8];
+  typename Epi::ColRegs cregs[DEPTH];
+#pragma unroll
+  for (int j = 0; j < DEPTH; ++j) {
+    const int col0 = n0 + (half + 2 * j) * 32;
+    if (FULL || col0 < shape.N) {
+      epi.load_col(col0 + 4 * fp, cregs[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (FULL || row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, col0 + 4 * fp, regs[j][i]);
+    }
+  }
+  mbar_wait(tfull, aph);
+  tc_fence_after();
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c = half + 2 * j;
+    const int col0 = n0 + c * 32;
+    if (!FULL && col0 >= shape.N) break;  // warp-uniform
+    float acc[32];
+    tmem_ld_32x32(taddr + c * 32, acc);
+    tmem_ld_wait();
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      st[lane * 8 + (p ^ (lane & 7))] = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + fr;
+      const float4 u = st[r * 8 + (fp ^ (r & 7))];
+      if (FULL || row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
+    }
+    if (j + DEPTH < NCH) {
+      const int coln = col0 + 64 * DEPTH;
+      if (FULL || coln < shape.N) {
+        epi.load_col(coln + 4 * fp, cregs[j % DEPTH]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (FULL || row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, coln + 4 * fp, regs[j % DEPTH][i]);
+      }
+    }
+  }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool FULL, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape,
                     Epi epi) {
@@ -116,6 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t kit = 0;
@@ -150,6 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
       uint32_t kit = 0, it = 0;
@@ -184,55 +277,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         umma_commit(&tfull_bar[as]);  // accumulator complete
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 4..11) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_EPI));
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // which of the quarter's two warps: even / odd chunks
+    const int half = (warp - 4) >> 2;        // which of the quarter's two warps: even / odd chunks
+    const int etid = threadIdx.x - 128;      // 0 .. 32 * GEMM_EPI_WARPS - 1
+    float4* st = reinterpret_cast<float4*>(sStage + (warp - 4) * 4096);  // [32 rows][8 x 16 B], piece ^= row & 7
     uint32_t it = 0;
+    // The functor's global operands of the first tile are pulled into L2 while its MMAs run; every later
+    // tile's are requested one tile ahead (the register prefetch inside a tile then only sees L2 latency).
+    if ((int)blockIdx.x < num_items) {
+      const int tile = blockIdx.x / shape.splits;
+      epi.prefetch((tile / n_tiles) * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
+    }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int tile = item / shape.splits;
       const uint32_t as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
-      const int row0 = m0 + quarter * 32;
-      float4* st = reinterpret_cast<float4*>(sStage + (warp - 2) * 4096);  // [32 rows][8 x 16 B], piece ^= row & 7
+      if (item + (int)gridDim.x < num_items) {
+        const int nt = (item + gridDim.x) / shape.splits;
+        if (nt != tile) epi.prefetch((nt / n_tiles) * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
+      }
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
-      const int fr = lane >> 3, fp = lane & 7;  // fragment i of this lane: row row0 + 4 i + fr, columns col0 + 4 fp ..
-      // Global operands of a chunk's 8 fragments are fetched (coalesced) one chunk ahead: the first chunk's
-      // while this tile's MMAs are still running, the next one's while the current chunk is written out.
-      typename Epi::Regs regs[8];
-      if (n0 + half * 32 < shape.N) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, n0 + half * 32 + 4 * fp, regs[i]);
-      }
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= shape.N) break;  // warp-uniform
-        float acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < 8; ++p)
-          st[lane * 8 + (p ^ (lane & 7))] = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + fr;
-          const float4 u = st[r * 8 + (fp ^ (r & 7))];
-          if (row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, regs[i]);
-        }
-        if (c + 2 < BN / 32 && col0 + 64 < shape.N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (row0 + 4 * i + fr < shape.M) epi.load(row0 + 4 * i + fr, col0 + 64 + 4 * fp, regs[i]);
-        }
-      }
+      epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -275,8 +347,10 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmShape shape, 
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     typename Epi::Regs regs;
+    typename Epi::ColRegs cregs;
+    epi.load_col(col0 + j, cregs);
     epi.load(row, col0 + j, regs);
-    epi.frag(row, col0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), regs);
+    epi.frag(row, col0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), regs, cregs);
   }
 }
 
@@ -312,10 +386,15 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   } else {
     MFAC_OK(make_tmap_bf16(&tmB, B.ptr, K, N, B.ld, 64, BN));
   }
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, Epi>;
+  // FULL: every tile lies inside the matrix, so the epilogue carries no row / column predicates (and half the code).
+  const bool full = (M % GEMM_BM == 0) && (N % BN == 0);
+  auto kern = full ? gemm_tcgen05_kernel<BN, A_MN, B_MN, true, Epi> : gemm_tcgen05_kernel<BN, A_MN, B_MN, false, Epi>;
   static bool configured = false;  // one per template instantiation
   if (!configured) {
-    MFAC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, true, Epi>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, false, Epi>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
@@ -383,11 +462,15 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
 // Plain epilogue used by the test hook and the weight-gradient GEMMs.
 struct EpiStoreF32 {
   static constexpr const char* name = "store_f32";
+  static constexpr int kPrefetchDepth = 1;
   struct Regs {};
+  struct ColRegs {};
   float* C;
   int64_t ldc;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int, ColRegs&) const {}
   __device__ __forceinline__ void load(int, int, Regs&) const {}
-  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&) const {
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs&) const {
     *reinterpret_cast<float4*>(C + (int64_t)row * ldc + col) = acc;
   }
 };

@@ -150,6 +150,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// L2 prefetch of a [128 rows x bn columns] tile of a row-major matrix (ES bytes per element, row stride ld
+// elements, 128-byte aligned rows), spread over `nthreads` threads; rows >= M are skipped.
+template <int ES>
+__device__ __forceinline__ void l2_prefetch_tile(const void* base, int64_t ld, int m0, int c0, int bn, int M, int tid,
+                                                 int nthreads) {
+  const int lines_per_row = (bn * ES) >> 7;
+  const int total = 128 * lines_per_row;
+  const char* b = reinterpret_cast<const char*>(base);
+  for (int i = tid; i < total; i += nthreads) {
+    const int r = i / lines_per_row, l = i - r * lines_per_row;
+    if (m0 + r < M) {
+      const char* p = b + ((int64_t)(m0 + r) * ld + c0) * ES + (l << 7);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------
