@@ -361,6 +361,241 @@ imdct512_kernel(const float* __restrict__ X, float* __restrict__ y, FftTables ta
   }
 }
 
+// ------------------------------------------------------------------ N = 512, hop = 256 fast path
+// The shipped configuration (window_size 512, hop N/2).  Sixteen lanes own one frame; each lane keeps 16 complex
+// points in registers and the 256-point FFT is two radix-16 passes with ONE 16x16 transpose through shared
+// memory (17-float2 row pitch: conflict free).  Every per-lane constant (window x pre-twiddle products, inter-pass
+// twiddles) lives in registers for the whole CTA; the post twiddles sit in shared memory.  The input segment of a
+// CTA's 32 frames is staged once, split into even / odd samples with a 16-word skew per 128 words, so the fold's
+// stride-2 reads become unit-stride and the two frames of a warp hit disjoint banks.  The interleaved DCT-IV output
+// X[2k] = Re y_k, X[2k+1] = -Im y_{255-k} is assembled with one lane-mirror shuffle per value and leaves the SM as
+// full 128-byte lines.  ~75 shared-memory wavefronts and ~400 issue slots per frame: HBM is the bound.
+constexpr int F2_THREADS = 128;
+constexpr int F2_FRAMES = 32;                  // frames per CTA (forward)
+constexpr int F2_EX = 16 * 17;                 // float2 per half-warp exchange buffer
+constexpr int F2_SEG_WORDS = ((F2_FRAMES - 1) * 128 + 512) / 128 * 144;  // skewed even (or odd) plane of a segment
+constexpr int I2_BLOCKS = 29;                  // 256-sample output blocks per CTA (inverse): 29 + 3 halo frames = 32
+constexpr int I2_FRAMES = I2_BLOCKS + 3;
+
+// forward 16-point DFT in registers: natural order in, output bin k at index 4 * (k % 4) + k / 4
+__device__ __forceinline__ void fft16(float2 (&x)[16]) {
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dft4(x[b], x[4 + b], x[8 + b], x[12 + b]);   // over a; t[b][c] at x[4c + b]
+  // t[b][c] *= W16^(b c)
+  x[5] = cmul(x[5], make_float2(c1, -s1));    // c=1,b=1
+  x[6] = cmul(x[6], make_float2(r, -r));      // c=1,b=2
+  x[7] = cmul(x[7], make_float2(s1, -c1));    // c=1,b=3
+  x[9] = cmul(x[9], make_float2(r, -r));      // c=2,b=1
+  x[10] = mul_mi(x[10]);                      // c=2,b=2  W16^4 = -i
+  x[11] = cmul(x[11], make_float2(-r, -r));   // c=2,b=3  W16^6
+  x[13] = cmul(x[13], make_float2(s1, -c1));  // c=3,b=1  W16^3
+  x[14] = cmul(x[14], make_float2(-r, -r));   // c=3,b=2  W16^6
+  x[15] = cmul(x[15], make_float2(-c1, s1));  // c=3,b=3  W16^9
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dft4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);  // over b; X[c + 4d] at x[4c + d]
+}
+__host__ __device__ constexpr int fidx(int k) { return 4 * (k & 3) + (k >> 2); }
+
+// c[j] holds point m = 16 j + ln on entry; on exit c[fidx(k2)] = FFT256(c)[ln + 16 k2] * post[ln + 16 k2]
+__device__ __forceinline__ void fft256_lanes16(float2 (&c)[16], const float2 (&tw)[16], float2* ex, const float2* s_post, int ln) {
+  fft16(c);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) c[fidx(k1)] = cmul(c[fidx(k1)], tw[k1]);
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) ex[k1 * 17 + ln] = c[fidx(k1)];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) c[n2] = ex[ln * 17 + n2];
+  fft16(c);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) c[fidx(k2)] = cmul(c[fidx(k2)], s_post[ln + 16 * k2]);
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 3)
+mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables tab, int64_t T, int64_t nf,
+                   int64_t x_clip_stride, int64_t X_clip_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* sE = reinterpret_cast<float*>(smem_raw);
+  float* sO = sE + F2_SEG_WORDS;
+  float2* sEx = reinterpret_cast<float2*>(sO + F2_SEG_WORDS);
+  float2* sPost = sEx + (F2_THREADS / 16) * F2_EX;
+  const int tid = threadIdx.x, lane = tid & 31, ln = tid & 15, hw = tid >> 4;
+  const int64_t b = blockIdx.y;
+  const int64_t f0 = (int64_t)blockIdx.x * F2_FRAMES;
+  const int nframes = (int)min((int64_t)F2_FRAMES, nf - f0);
+
+  // per-lane constants: (window x pre-twiddle) products of the 16 points this lane folds, inter-pass twiddles
+  float kf[16][4];
+  float2 tw[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int m = 16 * j + ln;
+    const float2 pre = tab.pre[m];
+    const float w1 = j < 8 ? tab.window[FFT_H + 2 * m] : tab.window[2 * m - FFT_H];
+    const float w2 = j < 8 ? tab.window[FFT_H - 1 - 2 * m] : tab.window[3 * FFT_H - 1 - 2 * m];
+    kf[j][0] = w1 * pre.x; kf[j][1] = w1 * pre.y; kf[j][2] = w2 * pre.x; kf[j][3] = w2 * pre.y;
+    tw[j] = tab.w256[(ln * j) & 255];
+  }
+  sPost[tid] = tab.post[tid];
+  sPost[tid + 128] = tab.post[tid + 128];
+
+  // stage the segment: even samples -> sE, odd -> sO, word q of a plane at q + 16 (q >> 7)
+  {
+    const int64_t s0 = f0 * FFT_H;
+    const int need = (nframes - 1) * FFT_H + 2 * FFT_N;
+    const float* xb = x + b * x_clip_stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xb + s0) & 15) == 0);
+    for (int i4 = tid * 4; i4 < need; i4 += F2_THREADS * 4) {
+      const int64_t s = s0 + i4;
+      float4 v;
+      if (vec && s + 3 < T) {
+        v = __ldg(reinterpret_cast<const float4*>(xb + s));
+      } else {
+        v.x = s < T ? __ldg(xb + s) : 0.f;
+        v.y = s + 1 < T ? __ldg(xb + s + 1) : 0.f;
+        v.z = s + 2 < T ? __ldg(xb + s + 2) : 0.f;
+        v.w = s + 3 < T ? __ldg(xb + s + 3) : 0.f;
+      }
+      const int q = i4 >> 1;
+      const int ph = q + 16 * (q >> 7);
+      *reinterpret_cast<float2*>(sE + ph) = make_float2(v.x, v.z);
+      *reinterpret_cast<float2*>(sO + ph) = make_float2(v.y, v.w);
+    }
+  }
+  __syncthreads();
+
+  float2* ex = sEx + hw * F2_EX;
+#pragma unroll 1
+  for (int it = 0; it < F2_FRAMES / (F2_THREADS / 16); ++it) {
+    const int f = it * (F2_THREADS / 16) + hw;
+    if (it * (F2_THREADS / 16) + (hw & ~1) >= nframes) break;  // warp-uniform: both of this warp's frames are out
+    const int fc = f < nframes ? f : nframes - 1;              // idle half-warp shadows a valid frame (no store)
+    const float* E = sE + fc * 144;
+    const float* O = sO + fc * 144;
+    float2 c[16];
+    // fold + window + pre-twiddle (constants folded):  plane index r -> r + 16 (r >> 7), 16-lane groups never straddle
+#define MFAC_SK(r) ((r) + 16 * ((r) >> 7))
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = O[MFAC_SK(383 - 16 * j) - ln], bb = E[MFAC_SK(384 + 16 * j) + ln];
+      const float cc = O[MFAC_SK(127 - 16 * j) - ln], d = E[MFAC_SK(128 + 16 * j) + ln];
+      c[j].x = -a * kf[j][0] - bb * kf[j][2] - cc * kf[j][3] + d * kf[j][1];
+      c[j].y = -a * kf[j][1] - bb * kf[j][3] + cc * kf[j][2] - d * kf[j][0];
+    }
+#pragma unroll
+    for (int j = 8; j < 16; ++j) {
+      const float p = E[MFAC_SK(16 * j - 128) + ln], q = O[MFAC_SK(383 - 16 * j) - ln];
+      const float r = E[MFAC_SK(128 + 16 * j) + ln], t = O[MFAC_SK(639 - 16 * j) - ln];
+      c[j].x = p * kf[j][0] - q * kf[j][2] + r * kf[j][3] + t * kf[j][1];
+      c[j].y = p * kf[j][1] - q * kf[j][3] - r * kf[j][2] - t * kf[j][0];
+    }
+#undef MFAC_SK
+    fft256_lanes16(c, tw, ex, sPost, ln);
+    // X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2
+    float2* dst = reinterpret_cast<float2*>(X + b * X_clip_stride + (f0 + fc) * FFT_N) + ln;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
+      if (f < nframes) dst[16 * k2] = make_float2(c[fidx(k2)].x, -im);
+    }
+  }
+}
+
+// inverse: CTA = clip b, output blocks [q0, q0 + I2_BLOCKS) of 256 samples; phase 1 DCT-IV of the <= 32 frames that
+// touch them into shared memory, phase 2 unfold + window + overlap-add as a float4 gather (4 frames per sample).
+__global__ void __launch_bounds__(F2_THREADS, 2)
+imdct512h256_kernel(const float* __restrict__ X, float* __restrict__ y, FftTables tab, int64_t nf, int64_t L,
+                    int64_t X_clip_stride, int64_t y_clip_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* sV = reinterpret_cast<float*>(smem_raw);                      // [I2_FRAMES][512]
+  float2* sEx = reinterpret_cast<float2*>(sV + I2_FRAMES * FFT_N);
+  float2* sPost = sEx + (F2_THREADS / 16) * F2_EX;
+  const int tid = threadIdx.x, ln = tid & 15, hw = tid >> 4;
+  const int64_t b = blockIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * I2_BLOCKS;
+  const int64_t nblocks = nf + 3;                                      // L / 256
+  const int64_t q1 = min(nblocks, q0 + I2_BLOCKS);
+  const int64_t i_lo = max((int64_t)0, q0 - 3), i_hi = min(nf - 1, q1 - 1);
+  const int nframes = (int)(i_hi - i_lo + 1);
+
+  float2 pre[16], tw[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    pre[j] = tab.pre[16 * j + ln];
+    tw[j] = tab.w256[(ln * j) & 255];
+  }
+  {
+    const float sc = 2.0f / FFT_N;
+    const float2 p0 = tab.post[tid], p1 = tab.post[tid + 128];
+    sPost[tid] = make_float2(p0.x * sc, p0.y * sc);
+    sPost[tid + 128] = make_float2(p1.x * sc, p1.y * sc);
+  }
+  __syncthreads();
+
+  float2* ex = sEx + hw * F2_EX;
+#pragma unroll 1
+  for (int it = 0; it < I2_FRAMES / (F2_THREADS / 16); ++it) {
+    const int f = it * (F2_THREADS / 16) + hw;
+    if (it * (F2_THREADS / 16) + (hw & ~1) >= nframes) break;
+    const int fc = f < nframes ? f : nframes - 1;
+    const float2* src = reinterpret_cast<const float2*>(X + b * X_clip_stride + (i_lo + fc) * FFT_N) + ln;
+    float2 c[16], in[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) in[j] = __ldg(src + 16 * j);          // {X[2m], X[2m+1]}, m = 16 j + ln
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // X[511 - 2m] = X[2 (255 - m) + 1]: second half of lane 15 - ln, register 15 - j
+      const float hi = __shfl_xor_sync(0xffffffffu, in[15 - j].y, 15);
+      c[j] = cmul(make_float2(in[j].x, hi), pre[j]);
+    }
+    fft256_lanes16(c, tw, ex, sPost, ln);
+    float2* dst = reinterpret_cast<float2*>(sV + fc * FFT_N) + ln;    // v[2k] = Re y_k, v[2k+1] = -Im y_{255-k}
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
+      if (f < nframes) dst[16 * k2] = make_float2(c[fidx(k2)].x, -im);
+    }
+  }
+  __syncthreads();
+
+  // gather: thread -> 4 consecutive samples r..r+3 of a block, two blocks per pass
+  const int r = 4 * (tid & 63);
+  float4 w0 = *reinterpret_cast<const float4*>(tab.window + r);
+  float4 w1 = *reinterpret_cast<const float4*>(tab.window + 256 + r);
+  float4 w2 = *reinterpret_cast<const float4*>(tab.window + 512 + r);
+  float4 w3 = *reinterpret_cast<const float4*>(tab.window + 768 + r);
+  float* yb = y + b * y_clip_stride;
+  const bool vec = (reinterpret_cast<uintptr_t>(yb) & 15) == 0;
+  for (int64_t q = q0 + (tid >> 6); q < q1; q += 2) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // frame i = q - t contributes its quarter t (n = r + 256 t)
+    if (q <= nf - 1) {                                   // t = 0:  v[256 + r + j]
+      const float4 v = *reinterpret_cast<const float4*>(sV + (q - i_lo) * FFT_N + 256 + r);
+      acc.x += v.x * w0.x; acc.y += v.y * w0.y; acc.z += v.z * w0.z; acc.w += v.w * w0.w;
+    }
+    if (q - 1 >= 0 && q - 1 <= nf - 1) {                 // t = 1: -v[511 - r - j]
+      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 1 - i_lo) * FFT_N + 508 - r);
+      acc.x -= v.w * w1.x; acc.y -= v.z * w1.y; acc.z -= v.y * w1.z; acc.w -= v.x * w1.w;
+    }
+    if (q - 2 >= 0 && q - 2 <= nf - 1) {                 // t = 2: -v[255 - r - j]
+      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 2 - i_lo) * FFT_N + 252 - r);
+      acc.x -= v.w * w2.x; acc.y -= v.z * w2.y; acc.z -= v.y * w2.z; acc.w -= v.x * w2.w;
+    }
+    if (q - 3 >= 0 && q - 3 <= nf - 1) {                 // t = 3: -v[r + j]
+      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 3 - i_lo) * FFT_N + r);
+      acc.x -= v.x * w3.x; acc.y -= v.y * w3.y; acc.z -= v.z * w3.z; acc.w -= v.w * w3.w;
+    }
+    float* dst = yb + q * 256 + r;
+    if (vec) *reinterpret_cast<float4*>(dst) = acc;
+    else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w; }
+  }
+}
+
+constexpr int F2_SMEM = 2 * F2_SEG_WORDS * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
+constexpr int I2_SMEM = I2_FRAMES * FFT_N * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
+
 // ------------------------------------------------------------------ generic N: dense contraction
 constexpr int DENSE_FR = 4;       // frames per CTA
 constexpr int DENSE_THREADS = 128;
@@ -429,6 +664,21 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
   fpc = fpc < 1 ? 1 : (fpc > 32 ? 32 : fpc);
   if (nf < fpc) fpc = (int)nf;
   const int64_t seg_len = (int64_t)(fpc - 1) * hop + 2 * FFT_N;
+  if (N == FFT_N && hop == FFT_H && io.in_elem_stride == 1 && io.out_elem_stride == FFT_N &&
+      (io.out_clip_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 7) == 0) {
+    MFAC_OK(get_tables(N, true, &ts));
+    static bool configured2 = false;
+    if (!configured2) {
+      MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+      configured2 = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(nf, F2_FRAMES), (unsigned)B);
+    void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)B * ((double)T + (double)nf * N), stream);
+    mdct512h256_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(x, X, ts.fft, T, nf, io.in_clip_stride, io.out_clip_stride);
+    profile_end(prof, stream);
+    count_launch();
+    return launch_status();
+  }
   if (N == FFT_N && seg_len <= 40960) {
     MFAC_OK(get_tables(N, true, &ts));
     const size_t smem = TABLE_BYTES + SCRATCH_BYTES + (size_t)seg_len * 4;
@@ -472,6 +722,21 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
   if (spc < 1024) spc = 1024;
   const int max_frames = (int)((spc - 1) / hop + (2 * FFT_N - 1) / hop + 2);
   const size_t smem = TABLE_BYTES + SCRATCH_BYTES + (size_t)max_frames * FFT_N * 4;
+  if (N == FFT_N && hop == FFT_H && io.out_elem_stride == 1 && io.in_elem_stride == FFT_N &&
+      (io.in_clip_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 7) == 0) {
+    MFAC_OK(get_tables(N, true, &ts));
+    static bool configured2 = false;
+    if (!configured2) {
+      MFAC_CUDA_OK(cudaFuncSetAttribute(imdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM));
+      configured2 = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(nf + 3, I2_BLOCKS), (unsigned)B);
+    void* prof = profile_begin(MFAC_PROF_IMDCT, 4.0 * (double)B * ((double)L + (double)nf * N), stream);
+    imdct512h256_kernel<<<grid, F2_THREADS, I2_SMEM, stream>>>(X, y, ts.fft, nf, L, io.in_clip_stride, io.out_clip_stride);
+    profile_end(prof, stream);
+    count_launch();
+    return launch_status();
+  }
   if (N == FFT_N && smem <= 160 * 1024) {  // tiny hops (< ~16) fall through to the dense path
     MFAC_OK(get_tables(N, true, &ts));
     static bool configured = false;
