@@ -398,7 +398,8 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
 __host__ __device__ constexpr int fidx(int k) { return 4 * (k & 3) + (k >> 2); }
 
 // c[j] holds point m = 16 j + ln on entry; on exit c[fidx(k2)] = FFT256(c)[ln + 16 k2] * post[ln + 16 k2]
-__device__ __forceinline__ void fft256_lanes16(float2 (&c)[16], const float2 (&tw)[16], float2* ex, const float2* s_post, int ln) {
+template <class PostT>
+__device__ __forceinline__ void fft256_lanes16(float2 (&c)[16], const float2 (&tw)[16], float2* ex, const PostT& post, int ln) {
   fft16(c);
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) c[fidx(k1)] = cmul(c[fidx(k1)], tw[k1]);
@@ -410,8 +411,16 @@ __device__ __forceinline__ void fft256_lanes16(float2 (&c)[16], const float2 (&t
   for (int n2 = 0; n2 < 16; ++n2) c[n2] = ex[ln * 17 + n2];
   fft16(c);
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) c[fidx(k2)] = cmul(c[fidx(k2)], s_post[ln + 16 * k2]);
+  for (int k2 = 0; k2 < 16; ++k2) c[fidx(k2)] = cmul(c[fidx(k2)], post(k2));
 }
+struct PostSmem {   // post twiddles in shared memory (forward: registers are spent on the fold constants)
+  const float2* p;
+  __device__ __forceinline__ float2 operator()(int k2) const { return p[16 * k2]; }
+};
+struct PostRegs {   // post twiddles in registers
+  float2 v[16];
+  __device__ __forceinline__ float2 operator()(int k2) const { return v[k2]; }
+};
 
 __global__ void __launch_bounds__(F2_THREADS, 3)
 mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables tab, int64_t T, int64_t nf,
@@ -426,7 +435,42 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
   const int64_t f0 = (int64_t)blockIdx.x * F2_FRAMES;
   const int nframes = (int)min((int64_t)F2_FRAMES, nf - f0);
 
-  // per-lane constants: (window x pre-twiddle) products of the 16 points this lane folds, inter-pass twiddles
+  // stage the segment: every thread first issues ALL of its 16-byte loads (one round trip), then splits them into
+  // the even plane sE and the odd plane sO; word q of a plane sits at q + 16 (q >> 7).  Samples >= T are zero.
+  {
+    const int64_t s0 = f0 * FFT_H;
+    const int need = (nframes - 1) * FFT_H + 2 * FFT_N;           // multiple of 256
+    const float* xb = x + b * x_clip_stride + s0;
+    constexpr int NV = (((F2_FRAMES - 1) * FFT_H + 2 * FFT_N) / 4 + F2_THREADS - 1) / F2_THREADS;  // float4 per thread
+    float4 v[NV];
+    if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0 && s0 + need <= T) {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int i4 = (tid + u * F2_THREADS) * 4;
+        v[u] = i4 < need ? __ldg(reinterpret_cast<const float4*>(xb + i4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int i4 = (tid + u * F2_THREADS) * 4;
+        const int64_t rem = T - s0 - i4;                          // samples available from this position
+        v[u].x = (i4 < need && rem > 0) ? __ldg(xb + i4) : 0.f;
+        v[u].y = (i4 < need && rem > 1) ? __ldg(xb + i4 + 1) : 0.f;
+        v[u].z = (i4 < need && rem > 2) ? __ldg(xb + i4 + 2) : 0.f;
+        v[u].w = (i4 < need && rem > 3) ? __ldg(xb + i4 + 3) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int q = (tid + u * F2_THREADS) * 2;
+      if (2 * q < need) {
+        const int ph = q + 16 * (q >> 7);
+        *reinterpret_cast<float2*>(sE + ph) = make_float2(v[u].x, v[u].z);
+        *reinterpret_cast<float2*>(sO + ph) = make_float2(v[u].y, v[u].w);
+      }
+    }
+  }
+  // per-lane constants
   float kf[16][4];
   float2 tw[16];
 #pragma unroll
@@ -441,37 +485,16 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
   sPost[tid] = tab.post[tid];
   sPost[tid + 128] = tab.post[tid + 128];
 
-  // stage the segment: even samples -> sE, odd -> sO, word q of a plane at q + 16 (q >> 7)
-  {
-    const int64_t s0 = f0 * FFT_H;
-    const int need = (nframes - 1) * FFT_H + 2 * FFT_N;
-    const float* xb = x + b * x_clip_stride;
-    const bool vec = ((reinterpret_cast<uintptr_t>(xb + s0) & 15) == 0);
-    for (int i4 = tid * 4; i4 < need; i4 += F2_THREADS * 4) {
-      const int64_t s = s0 + i4;
-      float4 v;
-      if (vec && s + 3 < T) {
-        v = __ldg(reinterpret_cast<const float4*>(xb + s));
-      } else {
-        v.x = s < T ? __ldg(xb + s) : 0.f;
-        v.y = s + 1 < T ? __ldg(xb + s + 1) : 0.f;
-        v.z = s + 2 < T ? __ldg(xb + s + 2) : 0.f;
-        v.w = s + 3 < T ? __ldg(xb + s + 3) : 0.f;
-      }
-      const int q = i4 >> 1;
-      const int ph = q + 16 * (q >> 7);
-      *reinterpret_cast<float2*>(sE + ph) = make_float2(v.x, v.z);
-      *reinterpret_cast<float2*>(sO + ph) = make_float2(v.y, v.w);
-    }
-  }
   __syncthreads();
 
   float2* ex = sEx + hw * F2_EX;
+  // CTA-uniform trip count (so the shuffles below need no reconvergence code); a half-warp whose frame lies beyond
+  // the clip shadows the last valid frame and skips the store
+  const int n_it = (nframes + F2_THREADS / 16 - 1) / (F2_THREADS / 16);
 #pragma unroll 1
-  for (int it = 0; it < F2_FRAMES / (F2_THREADS / 16); ++it) {
+  for (int it = 0; it < n_it; ++it) {
     const int f = it * (F2_THREADS / 16) + hw;
-    if (it * (F2_THREADS / 16) + (hw & ~1) >= nframes) break;  // warp-uniform: both of this warp's frames are out
-    const int fc = f < nframes ? f : nframes - 1;              // idle half-warp shadows a valid frame (no store)
+    const int fc = f < nframes ? f : nframes - 1;
     const float* E = sE + fc * 144;
     const float* O = sO + fc * 144;
     float2 c[16];
@@ -492,7 +515,7 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
       c[j].y = p * kf[j][1] - q * kf[j][3] - r * kf[j][2] - t * kf[j][0];
     }
 #undef MFAC_SK
-    fft256_lanes16(c, tw, ex, sPost, ln);
+    fft256_lanes16(c, tw, ex, PostSmem{sPost + ln}, ln);
     // X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2
     float2* dst = reinterpret_cast<float2*>(X + b * X_clip_stride + (f0 + fc) * FFT_N) + ln;
 #pragma unroll
@@ -511,7 +534,6 @@ imdct512h256_kernel(const float* __restrict__ X, float* __restrict__ y, FftTable
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* sV = reinterpret_cast<float*>(smem_raw);                      // [I2_FRAMES][512]
   float2* sEx = reinterpret_cast<float2*>(sV + I2_FRAMES * FFT_N);
-  float2* sPost = sEx + (F2_THREADS / 16) * F2_EX;
   const int tid = threadIdx.x, ln = tid & 15, hw = tid >> 4;
   const int64_t b = blockIdx.y;
   const int64_t q0 = (int64_t)blockIdx.x * I2_BLOCKS;
@@ -520,37 +542,45 @@ imdct512h256_kernel(const float* __restrict__ X, float* __restrict__ y, FftTable
   const int64_t i_lo = max((int64_t)0, q0 - 3), i_hi = min(nf - 1, q1 - 1);
   const int nframes = (int)(i_hi - i_lo + 1);
 
+  float2* ex = sEx + hw * F2_EX;
+  constexpr int HW = F2_THREADS / 16;
+  // the first frame's coefficients are requested before anything else; the constant tables load behind them
+  float2 in[16];
+  {
+    const int fc0 = hw < nframes ? hw : nframes - 1;
+    const float2* src = reinterpret_cast<const float2*>(X + b * X_clip_stride + (i_lo + fc0) * FFT_N) + ln;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) in[j] = __ldg(src + 16 * j);          // {X[2m], X[2m+1]}, m = 16 j + ln
+  }
   float2 pre[16], tw[16];
+  PostRegs post;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     pre[j] = tab.pre[16 * j + ln];
     tw[j] = tab.w256[(ln * j) & 255];
+    const float2 p = tab.post[ln + 16 * j];
+    post.v[j] = make_float2(p.x * (2.0f / FFT_N), p.y * (2.0f / FFT_N));
   }
-  {
-    const float sc = 2.0f / FFT_N;
-    const float2 p0 = tab.post[tid], p1 = tab.post[tid + 128];
-    sPost[tid] = make_float2(p0.x * sc, p0.y * sc);
-    sPost[tid + 128] = make_float2(p1.x * sc, p1.y * sc);
-  }
-  __syncthreads();
-
-  float2* ex = sEx + hw * F2_EX;
+  const int n_it = (nframes + HW - 1) / HW;                          // CTA-uniform
 #pragma unroll 1
-  for (int it = 0; it < I2_FRAMES / (F2_THREADS / 16); ++it) {
-    const int f = it * (F2_THREADS / 16) + hw;
-    if (it * (F2_THREADS / 16) + (hw & ~1) >= nframes) break;
+  for (int it = 0; it < n_it; ++it) {
+    const int f = it * HW + hw;
     const int fc = f < nframes ? f : nframes - 1;
-    const float2* src = reinterpret_cast<const float2*>(X + b * X_clip_stride + (i_lo + fc) * FFT_N) + ln;
-    float2 c[16], in[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) in[j] = __ldg(src + 16 * j);          // {X[2m], X[2m+1]}, m = 16 j + ln
+    float2 c[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       // X[511 - 2m] = X[2 (255 - m) + 1]: second half of lane 15 - ln, register 15 - j
       const float hi = __shfl_xor_sync(0xffffffffu, in[15 - j].y, 15);
       c[j] = cmul(make_float2(in[j].x, hi), pre[j]);
     }
-    fft256_lanes16(c, tw, ex, sPost, ln);
+    if (it + 1 < n_it) {                                               // next frame's coefficients fly during this FFT
+      const int fn = (it + 1) * HW + hw;
+      const int fcn = fn < nframes ? fn : nframes - 1;
+      const float2* src = reinterpret_cast<const float2*>(X + b * X_clip_stride + (i_lo + fcn) * FFT_N) + ln;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) in[j] = __ldg(src + 16 * j);
+    }
+    fft256_lanes16(c, tw, ex, post, ln);
     float2* dst = reinterpret_cast<float2*>(sV + fc * FFT_N) + ln;    // v[2k] = Re y_k, v[2k+1] = -Im y_{255-k}
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
@@ -568,33 +598,37 @@ imdct512h256_kernel(const float* __restrict__ X, float* __restrict__ y, FftTable
   float4 w3 = *reinterpret_cast<const float4*>(tab.window + 768 + r);
   float* yb = y + b * y_clip_stride;
   const bool vec = (reinterpret_cast<uintptr_t>(yb) & 15) == 0;
-  for (int64_t q = q0 + (tid >> 6); q < q1; q += 2) {
+  // local block index lb = q - q0; frame slot of (q - t) in sV is lb + off - t with off = q0 - i_lo (0..3)
+  const int nb = (int)(q1 - q0), off = (int)(q0 - i_lo);
+  const int lastf = (int)(nf - 1 - i_lo);                  // last valid frame slot
+  float* dst = yb + (q0 + (tid >> 6)) * 256 + r;
+  for (int lb = tid >> 6; lb < nb; lb += 2, dst += 512) {
+    const int sl = lb + off;                               // slot of frame q
+    const float* vb = sV + sl * FFT_N;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // frame i = q - t contributes its quarter t (n = r + 256 t)
-    if (q <= nf - 1) {                                   // t = 0:  v[256 + r + j]
-      const float4 v = *reinterpret_cast<const float4*>(sV + (q - i_lo) * FFT_N + 256 + r);
-      acc.x += v.x * w0.x; acc.y += v.y * w0.y; acc.z += v.z * w0.z; acc.w += v.w * w0.w;
+    if (sl <= lastf) {                                     // t = 0:  v[256 + r + j]
+      const float4 v = *reinterpret_cast<const float4*>(vb + 256 + r);
+      acc.x = v.x * w0.x; acc.y = v.y * w0.y; acc.z = v.z * w0.z; acc.w = v.w * w0.w;
     }
-    if (q - 1 >= 0 && q - 1 <= nf - 1) {                 // t = 1: -v[511 - r - j]
-      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 1 - i_lo) * FFT_N + 508 - r);
+    if (sl >= 1 && sl - 1 <= lastf) {                      // t = 1: -v[511 - r - j]
+      const float4 v = *reinterpret_cast<const float4*>(vb - FFT_N + 508 - r);
       acc.x -= v.w * w1.x; acc.y -= v.z * w1.y; acc.z -= v.y * w1.z; acc.w -= v.x * w1.w;
     }
-    if (q - 2 >= 0 && q - 2 <= nf - 1) {                 // t = 2: -v[255 - r - j]
-      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 2 - i_lo) * FFT_N + 252 - r);
+    if (sl >= 2 && sl - 2 <= lastf) {                      // t = 2: -v[255 - r - j]
+      const float4 v = *reinterpret_cast<const float4*>(vb - 2 * FFT_N + 252 - r);
       acc.x -= v.w * w2.x; acc.y -= v.z * w2.y; acc.z -= v.y * w2.z; acc.w -= v.x * w2.w;
     }
-    if (q - 3 >= 0 && q - 3 <= nf - 1) {                 // t = 3: -v[r + j]
-      const float4 v = *reinterpret_cast<const float4*>(sV + (q - 3 - i_lo) * FFT_N + r);
+    if (sl >= 3 && sl - 3 <= lastf) {                      // t = 3: -v[r + j]
+      const float4 v = *reinterpret_cast<const float4*>(vb - 3 * FFT_N + r);
       acc.x -= v.x * w3.x; acc.y -= v.y * w3.y; acc.z -= v.z * w3.z; acc.w -= v.w * w3.w;
     }
-    float* dst = yb + q * 256 + r;
     if (vec) *reinterpret_cast<float4*>(dst) = acc;
     else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w; }
   }
 }
 
 constexpr int F2_SMEM = 2 * F2_SEG_WORDS * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
-constexpr int I2_SMEM = I2_FRAMES * FFT_N * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
+constexpr int I2_SMEM = I2_FRAMES * FFT_N * 4 + (F2_THREADS / 16) * F2_EX * 8;
 
 // ------------------------------------------------------------------ generic N: dense contraction
 constexpr int DENSE_FR = 4;       // frames per CTA
