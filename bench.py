@@ -11,8 +11,8 @@ JVP, loss, backward) -> gradient all-reduce (N > 1) -> AdamW.  Workload = BASELI
 SURVEY.md R4 forces: the shipped noise_dimension=196608 needs 309 G parameters per block and cannot be
 instantiated anywhere, so noise_dimension is a flag (default 784 samples -> 2 MDCT frames -> D=1024, the
 geometry of the one runnable config); every other hyper-parameter is the config's.  The per-GPU batch is
-a flag too: the config's batch_size=128 is launch/optimizer-bound on a B200, so the default is the
-tensor-bound 4096 and the config-faithful 128 is reported next to it under "sweep".
+a flag too: the config's batch_size=128 is launch/optimizer-bound on a B200, so the default is 18944 (one
+128-row GEMM tile per SM and wave) and the config-faithful 128 is reported next to it under "sweep".
 
 Keys beyond the base contract: "roofline" (tcgen05 GEMM family, per-launch CUDA events), "cpu_baseline"
 (oracle port on the host cores), "e2e" (host buffers through the public Python API), "clocks", "codec"
@@ -264,21 +264,47 @@ def run_mfac(args):
     model, state, strat, tok, x_raw = main["objs"]
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D of the raw audio + D2H of the loss per step
-    x_host = x_raw.cpu().pin_memory()
-    for _ in range(2):
-        state, loss = step_fn(state, strat, tok, x_host.to(dev, non_blocking=True))
-        float(loss)
+    # Input pipeline: two pinned host batches, uploaded on a copy stream into two device buffers so that the upload of
+    # step i+1 overlaps the compute of step i; the loss is read back to the host every step.
+    x_host = [x_raw.cpu().pin_memory(), x_raw.flip(0).cpu().pin_memory()]
+    x_dev = [torch.empty_like(x_raw), torch.empty_like(x_raw)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])           # the step that last read this buffer has finished
+            x_dev[b].copy_(x_host[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_loop(n):
+        nonlocal state
+        for b in range(2):
+            consumed[b].record(torch.cuda.current_stream())
+        upload(0)
+        lv = None
+        for i in range(n):
+            b = i & 1
+            torch.cuda.current_stream().wait_event(ready[b])
+            if i + 1 < n:
+                upload(i + 1)
+            state, loss = step_fn(state, strat, tok, x_dev[b])
+            consumed[b].record(torch.cuda.current_stream())
+            lv = float(loss)  # device -> host read every step, like trainers/train.py:347
+        return lv
+
+    e2e_loop(2)
     torch.cuda.synchronize(); dp.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        xd = x_host.to(dev, non_blocking=True)
-        state, loss = step_fn(state, strat, tok, xd)
-        lv = float(loss)  # device -> host read every step, like trainers/train.py:347
+    e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
     dp.barrier()
-    e2e = {"value": B * world * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
-           "d2h_bytes_per_step": 4, "api": "MDCTTokenization.tokenize + train_step (ImprovedMeanFlowLoss) on pinned host input"}
+    e2e = {"value": B * world * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(x_host[0].numel() * 4),
+           "d2h_bytes_per_step": 4, "api": "MDCTTokenization.tokenize + train_step (ImprovedMeanFlowLoss); pinned host audio, "
+           "double-buffered upload on a copy stream, loss read back every step"}
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM): per-launch CUDA events on the launch stream
     roofline, families = None, None
@@ -378,9 +404,13 @@ def codec_bench(m, _lib, dev, pk):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[f"clips_{Bc}"] = {"audio_seconds_per_s": Bc * 10.0 / (ms * 1e-3), "ms": ms}
-    _lib.profile_enable(True)
-    x = 0.1 * torch.randn(256, T, device=dev)
+    x = 0.1 * torch.randn(256, T, device=dev)      # 451 MB in, 902 MB of coefficients: far beyond the 126 MB L2
     for _ in range(3):
+        X = m.mdct(x, N, hop)
+        y = m.imdct(X, N, hop)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    for _ in range(10):
         X = m.mdct(x, N, hop)
         y = m.imdct(X, N, hop)
     prof = _lib.profile_collect()
@@ -399,9 +429,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mfac", choices=["mfac", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=18944, help="per-GPU batch (148 SMs x 128-row tiles)")
     ap.add_argument("--noise-dimension", type=int, default=784, help="raw samples per example (T)")
-    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 18944])
+    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 4096])
     ap.add_argument("--quick", action="store_true", help="skip sweep / codec / cpu baseline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mfac":
