@@ -165,6 +165,64 @@ MFAC_API int mfac_sample(const MfacMlpDims* dims, const float* params, const voi
                 const float* noise, int32_t mode, int32_t n_steps, float guidance_scale, uint64_t seed, float* out,
                 int64_t B, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ MLP-Mixer / ConvNeXt velocity networks (forward)
+ * ref: ConditionalMLPMixerFlow models/mlp_mixer.py:171-235; ConditionalConvFlow models/conv_flow.py:213-271.
+ * Same call signature as the MLP flow: x[B,D], time[B,2], latents[B, latent_flat] (the reference's
+ * [B, num_latent_tokens, latent_dim] flattened, mlp_mixer.py:224-229) or NULL -> out[B,D].
+ * Weights are passed as device pointers: kernels bf16 [in,out] row-major (Flax layout), biases fp32.
+ * The block arrays are HOST arrays of structs holding device pointers.  Forward only (the reference never
+ * trains these models). */
+typedef struct MfacDense {
+  const void* w;   /* bf16 [in, out] */
+  const float* b;  /* fp32 [out] */
+} MfacDense;
+
+typedef struct MfacMixerDims {
+  int32_t D, C, nb;
+  int32_t tokens;      /* int(sqrt(D))^2 */
+  int32_t channels;    /* num_channels (8, 16 or 32) */
+  int32_t token_mix, channel_mix;
+  int32_t latent_flat; /* num_latent_tokens * latent_dim, 0 if latents are never passed */
+} MfacMixerDims;
+typedef struct MfacMixerBlockW {
+  MfacDense input_proj, adaln1, tok1, tok2, adaln2, ch1, ch2, output_proj;
+} MfacMixerBlockW;
+typedef struct MfacMixerWeights {
+  const MfacMixerBlockW* blocks; /* host array [nb] */
+  MfacDense latent_proj;
+} MfacMixerWeights;
+MFAC_API size_t mfac_mixer_workspace_bytes(const MfacMixerDims* dims, int64_t B);
+MFAC_API int mfac_mixer_forward(const MfacMixerDims* dims, const MfacMixerWeights* w, const float* x, const float* time,
+                       const float* latents, float* out, int64_t B, void* ws, size_t ws_bytes, void* stream);
+
+typedef struct MfacConvDims {
+  int32_t D, C, nb;
+  int32_t S;           /* int(sqrt(D)) */
+  int32_t channels;    /* min(16, C / 4): 4, 8 or 16 */
+  int32_t bottleneck;  /* 128 */
+  int32_t latent_flat;
+} MfacConvDims;
+typedef struct MfacConvBlockW {
+  MfacDense input_proj1, input_proj2, conditioning, output_proj1, output_proj2;
+  /* ConvNeXt block, all fp32 (the image stays in shared memory; SIMT fp32 arithmetic) */
+  const float* conv3_w;     /* [3, 3, ch, ch]  (kh, kw, in, out) */
+  const float* conv3_b;     /* [ch] */
+  const float* pw1_w;       /* [ch, 2ch] */
+  const float* pw1_b;       /* [2ch] */
+  const float* grn_gamma;   /* [2ch] or NULL (zeros) */
+  const float* grn_beta;    /* [2ch] or NULL */
+  const float* pw2_w;       /* [2ch, ch] */
+  const float* pw2_b;       /* [ch] */
+  const float* layer_scale; /* [ch] or NULL (ones) */
+} MfacConvBlockW;
+typedef struct MfacConvWeights {
+  const MfacConvBlockW* blocks; /* host array [nb] */
+  MfacDense latent_proj;
+} MfacConvWeights;
+MFAC_API size_t mfac_conv_workspace_bytes(const MfacConvDims* dims, int64_t B);
+MFAC_API int mfac_conv_forward(const MfacConvDims* dims, const MfacConvWeights* w, const float* x, const float* time,
+                      const float* latents, float* out, int64_t B, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ data-parallel gradient all-reduce
  * (absent in the reference).  id_bytes = the 128-byte ncclUniqueId. */
 MFAC_API int mfac_comm_unique_id(void* id_bytes_out);

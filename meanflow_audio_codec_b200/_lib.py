@@ -34,6 +34,36 @@ class ImfAux(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("v", "u", "dudt", "per_example", "e", "t", "r")]
 
 
+class Dense(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
+
+
+class MixerDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("D", "C", "nb", "tokens", "channels", "token_mix", "channel_mix", "latent_flat")]
+
+
+class MixerBlockW(C.Structure):
+    _fields_ = [(n, Dense) for n in ("input_proj", "adaln1", "tok1", "tok2", "adaln2", "ch1", "ch2", "output_proj")]
+
+
+class MixerWeights(C.Structure):
+    _fields_ = [("blocks", C.POINTER(MixerBlockW)), ("latent_proj", Dense)]
+
+
+class ConvDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("D", "C", "nb", "S", "channels", "bottleneck", "latent_flat")]
+
+
+class ConvBlockW(C.Structure):
+    _fields_ = ([(n, Dense) for n in ("input_proj1", "input_proj2", "conditioning", "output_proj1", "output_proj2")] +
+                [(n, C.c_void_p) for n in ("conv3_w", "conv3_b", "pw1_w", "pw1_b", "grn_gamma", "grn_beta", "pw2_w", "pw2_b",
+                                           "layer_scale")])
+
+
+class ConvWeights(C.Structure):
+    _fields_ = [("blocks", C.POINTER(ConvBlockW)), ("latent_proj", Dense)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -61,6 +91,10 @@ PROTOTYPES = {
     "mfac_adamw_step": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_sample": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I32, _I32, _F, C.c_uint64, _P, _I64, _P,
                               C.c_size_t, _P]),
+    "mfac_mixer_workspace_bytes": (C.c_size_t, [C.POINTER(MixerDims), _I64]),
+    "mfac_mixer_forward": (C.c_int, [C.POINTER(MixerDims), C.POINTER(MixerWeights), _P, _P, _P, _P, _I64, _P, C.c_size_t, _P]),
+    "mfac_conv_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDims), _I64]),
+    "mfac_conv_forward": (C.c_int, [C.POINTER(ConvDims), C.POINTER(ConvWeights), _P, _P, _P, _P, _I64, _P, C.c_size_t, _P]),
     "mfac_comm_unique_id": (C.c_int, [_P]),
     "mfac_comm_init": (C.c_int, [_P, _I32, _I32]),
     "mfac_comm_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),

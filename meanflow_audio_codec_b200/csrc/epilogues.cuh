@@ -1,0 +1,215 @@
+// Fused GEMM epilogue functors shared by the MLP flow (imf.cu) and the mixer / convnet forwards (flows.cu).
+// Contract: see gemm.cuh ("Epilogue contract").
+#pragma once
+
+#include "mfac_common.cuh"
+
+namespace mfac {
+
+constexpr float LN_EPS = 1e-6f;  // flax.linen.LayerNorm(epsilon=1e-6)
+
+// ---------------------------------------------------------------------------------------
+// fused GEMM epilogues: frag(row, col, acc) handles 4 consecutive columns of one output row; 8 adjacent
+// lanes cover 32 columns of the same row, so every access below is sector/line coalesced (see gemm.cuh).
+// Read-only operands go through ld.global.nc so the 8 unrolled fragments' loads are issued back to back.
+// GELU uses tanh.approx.f32 (one MUFU op): its 2^-11 relative error is far inside the bf16 rounding of
+// the values it feeds.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_fast(float a) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * a * (1.0f + tanh_fast(k0 * (a + k1 * a * a * a)));
+}
+__device__ __forceinline__ float dgelu_fast(float a) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float th = tanh_fast(k0 * (a + k1 * a * a * a));
+  return 0.5f * (1.0f + th) + 0.5f * a * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * a * a);
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg_bf4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 ldg_bf4_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 bf4_to_f4(uint2 u) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+constexpr int EPI_THREADS = 256;  // epilogue threads of the GEMM kernel (prefetch work split)
+struct BiasCol { float4 b; };
+struct NoRegs {};
+
+// g = gelu(acc + bias); optionally keeps the pre-activation a (bf16) for the tangent/backward.
+struct EpiBiasGelu {
+  static constexpr const char* name = "bias_gelu";
+  static constexpr int kPrefetchDepth = 1;
+  const float* bias;        // padded fp32 [N]
+  __nv_bfloat16* g;         // [M, ld]
+  __nv_bfloat16* a_out;     // [M, ld] or null
+  int64_t ld;
+  using Regs = NoRegs;
+  using ColRegs = BiasCol;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = ldg_f4(bias + col); }
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
+    acc = add4(acc, c.b);
+    const int64_t at = (int64_t)row * ld + col;
+    if (a_out) st_bf4(a_out + at, acc);
+    st_bf4(g + at, make_float4(gelu_fast(acc.x), gelu_fast(acc.y), gelu_fast(acc.z), gelu_fast(acc.w)));
+  }
+};
+// out = acc * gelu'(a)   (tangent through GELU, and the backward of GELU)
+struct EpiMulDgelu {
+  static constexpr const char* name = "mul_dgelu";
+  static constexpr int kPrefetchDepth = 2;
+  const __nv_bfloat16* a;   // [M, ld]
+  __nv_bfloat16* out;       // [M, ld]
+  int64_t ld;
+  struct Regs { uint2 av; };
+  using ColRegs = NoRegs;
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+    l2_prefetch_tile<2>(a, ld, m0, n0, bn, M, etid, EPI_THREADS);
+  }
+  __device__ __forceinline__ void load_col(int, ColRegs&) const {}
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const { r.av = ldg_bf4_raw(a + (int64_t)row * ld + col); }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r, const ColRegs&) const {
+    const int64_t at = (int64_t)row * ld + col;
+    const float4 av = bf4_to_f4(r.av);
+    st_bf4(out + at, make_float4(acc.x * dgelu_fast(av.x), acc.y * dgelu_fast(av.y), acc.z * dgelu_fast(av.z),
+                                 acc.w * dgelu_fast(av.w)));
+  }
+};
+// out = acc (+ bias)
+struct EpiLinearBf16 {
+  static constexpr const char* name = "linear_bf16";
+  static constexpr int kPrefetchDepth = 1;
+  const float* bias;  // or null
+  __nv_bfloat16* out;
+  int64_t ld;
+  using Regs = NoRegs;
+  using ColRegs = BiasCol;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
+    st_bf4(out + (int64_t)row * ld + col, add4(acc, c.b));
+  }
+};
+struct EpiLinearF32 {
+  static constexpr const char* name = "linear_f32";
+  static constexpr int kPrefetchDepth = 1;
+  const float* bias;  // or null
+  float* out;
+  int64_t ld;
+  using Regs = NoRegs;
+  using ColRegs = BiasCol;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
+    st_f4(out + (int64_t)row * ld + col, add4(acc, c.b));
+  }
+};
+// out = (acc + bias) * alpha + res   (fp32 and/or bf16 copy); res may be null.  Residual adds of the mixer / convnet
+// blocks: x / num_blocks + residual  (mlp_mixer.py:163, conv_flow.py:205) and the mixer's inner skip connections.
+struct EpiAffineResidual {
+  static constexpr const char* name = "affine_residual";
+  static constexpr int kPrefetchDepth = 2;
+  const float* bias;       // [N] or null
+  const float* res;        // [M, ld] or null
+  float* out_f;            // [M, ld] or null (may alias res)
+  __nv_bfloat16* out_b;    // [M, ld] or null
+  int64_t ld;
+  float alpha;
+  struct Regs { float4 r; };
+  using ColRegs = BiasCol;
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+    if (res && (ld & 31) == 0) l2_prefetch_tile<4>(res, ld, m0, n0, bn, M, etid, EPI_THREADS);
+  }
+  __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const {
+    r.r = res ? *reinterpret_cast<const float4*>(res + (int64_t)row * ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r, const ColRegs& c) const {
+    const int64_t at = (int64_t)row * ld + col;
+    const float4 v = make_float4((acc.x + c.b.x) * alpha + r.r.x, (acc.y + c.b.y) * alpha + r.r.y,
+                                 (acc.z + c.b.z) * alpha + r.r.z, (acc.w + c.b.w) * alpha + r.r.w);
+    if (out_f) st_f4(out_f + at, v);
+    if (out_b) st_bf4(out_b + at, v);
+  }
+};
+// block output: o = acc + b2;  x_new = o (1 + s2) / nb + x_old      (mlp_flow.py:112-117)
+struct EpiBlockOut {
+  static constexpr const char* name = "block_out";
+  static constexpr int kPrefetchDepth = 2;
+  const float* bias;          // padded [Dp]
+  const __nv_bfloat16* m;     // [M, Mp]; s2 at column offset s2_off
+  const float* x_old;         // [M, Dp]
+  float* x_new;               // [M, Dp] (may alias x_old: each element is read and written by the same thread)
+  __nv_bfloat16* o_out;       // [M, Dp] or null
+  int64_t ldm, ldx;
+  int s2_off;
+  float inv_nb;
+  struct Regs { uint2 s2; float4 xo; };
+  using ColRegs = BiasCol;
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+    l2_prefetch_tile<2>(m, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
+    l2_prefetch_tile<4>(x_old, ldx, m0, n0, bn, M, etid, EPI_THREADS);
+  }
+  __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = ldg_f4(bias + col); }
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const {
+    r.s2 = ldg_bf4_raw(m + (int64_t)row * ldm + s2_off + col);
+    r.xo = ldg_f4(x_old + (int64_t)row * ldx + col);
+  }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r, const ColRegs& c) const {
+    const int64_t at = (int64_t)row * ldx + col;
+    const float4 s2 = bf4_to_f4(r.s2), xo = r.xo;
+    acc = add4(acc, c.b);
+    if (o_out) st_bf4(o_out + at, acc);
+    st_f4(x_new + at, make_float4(acc.x * ((1.0f + s2.x) * inv_nb) + xo.x, acc.y * ((1.0f + s2.y) * inv_nb) + xo.y,
+                                  acc.z * ((1.0f + s2.z) * inv_nb) + xo.z, acc.w * ((1.0f + s2.w) * inv_nb) + xo.w));
+  }
+};
+// tangent of the block output: xd_new = (od (1+s2) + o s2d) / nb + xd_old
+struct EpiBlockOutTangent {
+  static constexpr const char* name = "block_out_tangent";
+  static constexpr int kPrefetchDepth = 1;
+  const __nv_bfloat16* m;     // primal modulation  [M, Mp]
+  const __nv_bfloat16* md;    // tangent modulation [M, Mp]
+  const __nv_bfloat16* o;     // primal o [M, Dp]
+  const float* xd_old;
+  float* xd_new;
+  int64_t ldm, ldx;
+  int s2_off;
+  float inv_nb;
+  struct Regs { uint2 s2, s2d, ov; float4 xd; };
+  using ColRegs = NoRegs;
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+    l2_prefetch_tile<2>(m, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
+    l2_prefetch_tile<2>(md, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
+    l2_prefetch_tile<2>(o, ldx, m0, n0, bn, M, etid, EPI_THREADS);
+    l2_prefetch_tile<4>(xd_old, ldx, m0, n0, bn, M, etid, EPI_THREADS);
+  }
+  __device__ __forceinline__ void load_col(int, ColRegs&) const {}
+  __device__ __forceinline__ void load(int row, int col, Regs& r) const {
+    const int64_t at = (int64_t)row * ldx + col, am = (int64_t)row * ldm + s2_off + col;
+    r.s2 = ldg_bf4_raw(m + am); r.s2d = ldg_bf4_raw(md + am); r.ov = ldg_bf4_raw(o + at); r.xd = ldg_f4(xd_old + at);
+  }
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r, const ColRegs&) const {
+    const int64_t at = (int64_t)row * ldx + col;
+    const float4 s2 = bf4_to_f4(r.s2), s2d = bf4_to_f4(r.s2d), ov = bf4_to_f4(r.ov), xd = r.xd;
+    st_f4(xd_new + at, make_float4((acc.x * (1.0f + s2.x) + ov.x * s2d.x) * inv_nb + xd.x,
+                                   (acc.y * (1.0f + s2.y) + ov.y * s2d.y) * inv_nb + xd.y,
+                                   (acc.z * (1.0f + s2.z) + ov.z * s2d.z) * inv_nb + xd.z,
+                                   (acc.w * (1.0f + s2.w) + ov.w * s2d.w) * inv_nb + xd.w));
+  }
+};
+
+}  // namespace mfac

@@ -26,7 +26,7 @@
 // directly with no transposed copies.
 //
 // Out-of-bounds rows / K tails are zero-filled by TMA; the epilogue is only invoked for
-// rows < M and 32-column groups that start below N (N must be a multiple of 32).
+// rows < M and 4-column fragments that start below N (N must be a multiple of 4).
 #pragma once
 
 #include <cmath>
@@ -105,7 +105,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& s
       for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + fr;
         const float4 u = st[r * 8 + (fp ^ (r & 7))];
-        if (row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, nr, nc);
+        if (row0 + r < shape.M && col0 + 4 * fp < shape.N) epi.frag(row0 + r, col0 + 4 * fp, u, nr, nc);
       }
     }
     return;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& s
 #pragma unroll
   for (int j = 0; j < DEPTH; ++j) {
     const int col0 = n0 + (half + 2 * j) * 32;
-    if (FULL || col0 < shape.N) {
+    if (FULL || col0 + 4 * fp < shape.N) {   // N may be any multiple of 4: the last chunk can be partial
       epi.load_col(col0 + 4 * fp, cregs[j]);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -142,11 +142,12 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& s
     for (int i = 0; i < 8; ++i) {
       const int r = 4 * i + fr;
       const float4 u = st[r * 8 + (fp ^ (r & 7))];
-      if (FULL || row0 + r < shape.M) epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
+      if (FULL || (row0 + r < shape.M && col0 + 4 * fp < shape.N))
+        epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
     }
     if (j + DEPTH < NCH) {
       const int coln = col0 + 64 * DEPTH;
-      if (FULL || coln < shape.N) {
+      if (FULL || coln + 4 * fp < shape.N) {
         epi.load_col(coln + 4 * fp, cregs[j % DEPTH]);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -413,7 +414,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   return launch_status();
 }
 
-// C = A * B with the given epilogue.  N must be a multiple of 32; K and M are arbitrary
+// C = A * B with the given epilogue.  N must be a multiple of 4; K and M are arbitrary
 // (TMA zero-fills), leading dimensions must be multiples of 8 elements (16-byte TMA strides).
 // split_k = true lets the launcher slice K so that (tiles x slices) covers the machine; the epilogue
 // must then accumulate atomically (Epi::kAtomic) into a zero-initialised output.
@@ -421,7 +422,7 @@ template <bool A_MN, bool B_MN, class Epi>
 int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
                 cudaStream_t stream, int force_bn = 0, bool split_k = false) {
   if (M <= 0 || N <= 0 || K <= 0) return MFAC_ERR_BAD_SHAPE;
-  if (N % 32 != 0 || A.ld % 8 != 0 || B.ld % 8 != 0) return MFAC_ERR_UNSUPPORTED;
+  if (N % 4 != 0 || A.ld % 8 != 0 || B.ld % 8 != 0) return MFAC_ERR_UNSUPPORTED;
   if (A.mn_major != A_MN || B.mn_major != B_MN) return MFAC_ERR_UNSUPPORTED;
   if (simt_gemm_enabled()) {
     SimtOperand a{reinterpret_cast<const __nv_bfloat16*>(A.ptr), A.ld, A_MN ? 1 : 0};

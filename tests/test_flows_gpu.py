@@ -1,0 +1,91 @@
+"""GPU parity of the MLP-Mixer and ConvNeXt velocity networks (forward) against the NumPy oracle (oracle/flows_np.py).
+Tolerance: 1e-2 rel-L2 of the block update (out - x) for bf16 operands with fp32 accumulation (BASELINE.json north_star).
+Reference: models/mlp_mixer.py:171-235, models/conv_flow.py:213-271.  Parity unpinned (no reference numbers exist)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    import meanflow_audio_codec_b200 as mod
+    return mod
+
+
+def tree_np(t):
+    return {k: (tree_np(v) if isinstance(v, dict) else v.detach().cpu().numpy().astype(np.float64)) for k, v in t.items()}
+
+
+def perturb(t, gen, scale=0.05):
+    """biases / GRN / layer-scale are zero- or 1e-6-initialised in Flax; give them weight so the test sees them"""
+    for k, v in t.items():
+        if isinstance(v, dict):
+            perturb(v, gen, scale)
+        elif k in ("bias", "gamma", "beta"):
+            v.copy_(scale * torch.randn(v.shape, generator=gen).to(v.device))
+        elif k == "layer_scale_gamma":
+            v.copy_((0.5 + 0.1 * torch.randn(v.shape, generator=gen)).to(v.device))
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("D,C,nb,tm,cm,ch,B,with_lat", [
+    (64, 32, 2, 64, 64, 16, 5, True),
+    (64, 32, 1, 128, 96, 8, 3, False),
+    (1024, 128, 2, 2048, 2048, 16, 4, True),     # the reference's default widths at D = 1024
+])
+def test_mixer_forward(m, D, C, nb, tm, cm, ch, B, with_lat):
+    from oracle import flows_np
+    model = m.ConditionalMLPMixerFlow(D, C, nb, latent_dimension=8, token_mix_dim=tm, channel_mix_dim=cm, num_channels=ch,
+                                      num_latent_tokens=4)
+    params = model.init(3)["params"]
+    gen = torch.Generator().manual_seed(5)
+    perturb(params, gen)
+    x = torch.randn(B, D, generator=gen).cuda()
+    time = torch.rand(B, 2, generator=gen).cuda()
+    lat = torch.randn(B, 4, 8, generator=gen).cuda() if with_lat else None
+    out = model.apply({"params": params}, x, time, lat).cpu().numpy().astype(np.float64)
+    ref = flows_np.mixer_forward(tree_np(params), x.cpu().numpy().astype(np.float64), time.cpu().numpy().astype(np.float64),
+                                 None if lat is None else lat.cpu().numpy().astype(np.float64),
+                                 num_blocks=nb, num_channels=ch, condition_dimension=C)
+    xn = x.cpu().numpy().astype(np.float64)
+    assert rel(out - xn, ref - xn) < 1e-2
+    assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("D,C,nb,B,with_lat", [
+    (64, 32, 2, 5, True),        # S = 8, channels = 8
+    (256, 16, 1, 3, False),      # S = 16, channels = 4
+    (1024, 128, 2, 4, True),     # S = 32, channels = 16 (the reference geometry at D = 1024)
+])
+def test_conv_forward(m, D, C, nb, B, with_lat):
+    from oracle import flows_np
+    model = m.ConditionalConvFlow(D, C, nb, latent_dimension=8, num_latent_tokens=4)
+    params = model.init(7)["params"]
+    gen = torch.Generator().manual_seed(9)
+    perturb(params, gen)
+    x = torch.randn(B, D, generator=gen).cuda()
+    time = torch.rand(B, 2, generator=gen).cuda()
+    lat = torch.randn(B, 4, 8, generator=gen).cuda() if with_lat else None
+    out = model.apply({"params": params}, x, time, lat).cpu().numpy().astype(np.float64)
+    ref = flows_np.conv_forward(tree_np(params), x.cpu().numpy().astype(np.float64), time.cpu().numpy().astype(np.float64),
+                                None if lat is None else lat.cpu().numpy().astype(np.float64),
+                                num_blocks=nb, condition_dimension=C)
+    xn = x.cpu().numpy().astype(np.float64)
+    assert rel(out - xn, ref - xn) < 1e-2
+    assert rel(out, ref) < 1e-2
+
+
+def test_factory_dispatch(m):
+    class Cfg:
+        noise_dimension, condition_dimension, num_blocks, latent_dimension = 64, 32, 1, 8
+    for arch, cls in (("mlp", m.ConditionalFlow), ("mlp_mixer", m.ConditionalMLPMixerFlow), ("convnet", m.ConditionalConvFlow), (None, m.ConditionalFlow)):
+        Cfg.architecture = arch
+        assert isinstance(m.create_flow_model(Cfg), cls)
+    Cfg.architecture = "transformer"
+    with pytest.raises(ValueError):
+        m.create_flow_model(Cfg)
