@@ -226,13 +226,22 @@ def run_mfac(args):
         x_raw = 0.1 * torch.randn(B, T, device=dev, generator=g)
         return model, state, strat, tok, x_raw
 
-    def step_fn(state, strat, tok, x_raw, key=0):
+    def step_fn_eager(state, strat, tok, x_raw, key=0):
         x = tok.tokenize(x_raw).reshape(x_raw.shape[0], -1)
         state, loss, _ = train_step_dp(dp, state, key, x, strat)
         return state, loss
 
-    def timed(B, steps, warmup, sample_clocks=False):
+    step_fn = step_fn_eager
+
+    def timed(B, steps, warmup, sample_clocks=False, graphed=False):
         model, state, strat, tok, x_raw = make(B)
+        if graphed:   # the whole step (tokenise + loss/grad + AdamW) as ONE CUDA-graph launch; single GPU only
+            gstep = m.GraphedTrainStep(state, strat, tok, x_raw, key=0)
+
+            def step_fn(state, strat, tok, x_raw, key=0):  # noqa: F811
+                return state, gstep(x_raw)
+        else:
+            step_fn = step_fn_eager
         for _ in range(warmup):
             state, loss = step_fn(state, strat, tok, x_raw)
         torch.cuda.synchronize()
@@ -350,7 +359,14 @@ def run_mfac(args):
                                            "tensor_frac_whole_step": flops_per_sample(D) * b / (r["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"]}
             del r
             torch.cuda.empty_cache()
+            if b <= 1024:   # launch-bound sizes: the same step replayed as one CUDA graph
+                r = timed(b, ks * 4, max(3, args.warmup), graphed=True)
+                sweep[f"per_gpu_batch_{b}_cuda_graph"] = {"samples_per_s": b * ks * 4 / (r["ms_total"] * 1e-3),
+                                                          "ms_per_step": r["ms_per_step"], "graph_launches_per_step": 1}
+                del r
+                torch.cuda.empty_cache()
         codec = codec_bench(m, _lib, dev, pk)
+        codec["other_architectures_forward"] = flows_bench(m, dev)
         cpu_baseline = time_cpu_reference(T, min(B, 128), 50, 1, budget_s=20.0)
         cpu_baseline.pop("ms_per_step", None)
 
@@ -420,6 +436,33 @@ def codec_bench(m, _lib, dev, pk):
         gbs = v["work"] / (v["ms"] * 1e-3) / 1e9
         out[fam] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                     "clips": 256, "ms_per_launch": v["ms"] / v["launches"]}
+    return out
+
+
+def flows_bench(m, dev):
+    """BASELINE configs[2]/[3]: forward-only velocity throughput of the mixer and convnet flows at D=1024."""
+    import torch
+    out = {}
+    for name, cls, Bf in (("mlp_mixer", m.ConditionalMLPMixerFlow, 256), ("convnet", m.ConditionalConvFlow, 2048)):
+        model = cls(1024, CFG["condition_dimension"], CFG["num_blocks"], CFG["latent_dimension"])
+        params = model.init(CFG["seed"], device=dev)["params"]
+        g = torch.Generator(device=dev).manual_seed(1)
+        x = torch.randn(Bf, 1024, device=dev, generator=g)
+        t = torch.rand(Bf, 2, device=dev, generator=g)
+        lat = torch.randn(Bf, 32, CFG["latent_dimension"], device=dev, generator=g)
+        for _ in range(3):
+            y = model.apply({"params": params}, x, t, lat)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            y = model.apply({"params": params}, x, t, lat)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"rows_per_s": Bf / (ms * 1e-3), "ms": ms, "batch": Bf, "blocks": CFG["num_blocks"], "D": 1024}
+        del model, params, x, lat, y
+        torch.cuda.empty_cache()
     return out
 
 

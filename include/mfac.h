@@ -130,6 +130,8 @@ typedef struct MfacImfConfig {
   uint64_t seed;
   uint64_t step;
   uint64_t row_offset;                 /* global index of local row 0 (rank * B) for the RNG */
+  const uint64_t* step_dev;            /* optional DEVICE counter read instead of `step` (CUDA-graph replay: the
+                                          captured launch must see a step that advances); NULL = use `step` */
 } MfacImfConfig;
 
 typedef struct MfacImfAux {
@@ -153,6 +155,13 @@ MFAC_API int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cf
 MFAC_API int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
                     int64_t count, float lr, float b1, float b2, float eps, float weight_decay, float grad_scale,
                     void* stream);
+
+/* Graph-capturable form: the step count lives in device memory.  *count_dev is read for the bias correction and
+ * then incremented on the device, so one captured launch sequence can be replayed step after step.
+ * scratch_dev: 2 floats of device scratch (bias-correction factors). */
+MFAC_API int mfac_adamw_step_dev(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
+                        uint64_t* count_dev, float* scratch_dev, float lr, float b1, float b2, float eps, float weight_decay,
+                        float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------ samplers
  * MFAC_SAMPLE_HEUN  ref: evaluators/sampling.py:5-95 (h = 0, grid linspace(1,0,n), dt = 1/n).

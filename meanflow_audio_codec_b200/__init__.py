@@ -12,4 +12,5 @@ from .mlp_flow import AdamW, ConditionalFlow, TrainState, adamw  # noqa: F401
 from .loss_strategies import (ImprovedMeanFlowLoss, LinearNoiseSchedule, LossStrategy,  # noqa: F401
                               MeanFlowTimeSampling, train_step)
 from .sampling import sample, sample_mean_flow  # noqa: F401
+from .graphs import GraphedTrainStep  # noqa: F401
 from .flows import ConditionalConvFlow, ConditionalMLPMixerFlow, create_flow_model  # noqa: F401

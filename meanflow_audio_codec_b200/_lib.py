@@ -27,6 +27,7 @@ class ImfConfig(C.Structure):
         ("data_proportion", C.c_float), ("loss_c", C.c_float),
         ("use_weighted_loss", C.c_int32),
         ("seed", C.c_uint64), ("step", C.c_uint64), ("row_offset", C.c_uint64),
+        ("step_dev", C.c_void_p),
     ]
 
 
@@ -89,6 +90,7 @@ PROTOTYPES = {
     "mfac_imf_loss_grad": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), _P, _P, _P, _P, _P, _P, _P, _P,
                                      C.POINTER(ImfAux), _I64, _P, C.c_size_t, _P]),
     "mfac_adamw_step": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
+    "mfac_adamw_step_dev": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_sample": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I32, _I32, _F, C.c_uint64, _P, _I64, _P,
                               C.c_size_t, _P]),
     "mfac_mixer_workspace_bytes": (C.c_size_t, [C.POINTER(MixerDims), _I64]),

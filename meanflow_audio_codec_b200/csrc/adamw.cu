@@ -35,12 +35,22 @@ struct AdamArgs {
   __nv_bfloat16* sw;  // may be null
   float* sb;
   float lr, b1, b2, eps, wd, gscale, inv_bc1, inv_bc2;
+  const float* bc_dev;  // optional {inv_bc1, inv_bc2} in device memory (graph replay)
 };
+
+// t = *count + 1;  bc = {1 / (1 - b1^t), 1 / (1 - b2^t)};  ++*count
+__global__ void adamw_bias_correction_kernel(uint64_t* count, float* bc, float b1, float b2) {
+  const double t = (double)(*count) + 1.0;
+  bc[0] = (float)(1.0 / (1.0 - pow((double)b1, t)));
+  bc[1] = (float)(1.0 / (1.0 - pow((double)b2, t)));
+  *count += 1;
+}
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= d.total) return;
   float p[4], g[4], m[4], v[4];
+  const float inv_bc1 = a.bc_dev ? a.bc_dev[0] : a.inv_bc1, inv_bc2 = a.bc_dev ? a.bc_dev[1] : a.inv_bc2;
   const bool full = i0 + 4 <= d.total;
   if (full) {
     const float4 p4 = *reinterpret_cast<const float4*>(a.p + i0), g4 = *reinterpret_cast<const float4*>(a.g + i0);
@@ -61,7 +71,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d) {
     const float gq = g[q] * a.gscale;
     m[q] = a.b1 * m[q] + (1.0f - a.b1) * gq;
     v[q] = a.b2 * v[q] + (1.0f - a.b2) * gq * gq;
-    const float upd = (m[q] * a.inv_bc1) / (sqrtf(v[q] * a.inv_bc2) + a.eps) + a.wd * p[q];
+    const float upd = (m[q] * inv_bc1) / (sqrtf(v[q] * inv_bc2) + a.eps) + a.wd * p[q];
     p[q] = p[q] - a.lr * upd;
   }
   if (full) {
@@ -133,13 +143,15 @@ int mfac_mlp_cast_params(const MfacMlpDims* dims, const float* params, void* sha
   return mfac::launch_status();
 }
 
-int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
-                    int64_t count, float lr, float b1, float b2, float eps, float weight_decay, float grad_scale,
-                    void* stream) {
+namespace {
+int adamw_launch(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow, int64_t count,
+                 uint64_t* count_dev, float* scratch_dev, float lr, float b1, float b2, float eps, float weight_decay,
+                 float grad_scale, void* stream) {
   mfac::Dims d;
   MFAC_OK(mfac::make_dims(dims, &d));
   if (!params || !grads || !mu || !nu) return MFAC_ERR_NULL;
   if (count < 0) return MFAC_ERR_BAD_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
   mfac::AdamArgs a;
   a.p = params; a.g = grads; a.mu = mu; a.nu = nu;
   a.sw = reinterpret_cast<__nv_bfloat16*>(shadow);
@@ -148,13 +160,35 @@ int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, 
   const double c = (double)count + 1.0;
   a.inv_bc1 = (float)(1.0 / (1.0 - std::pow((double)b1, c)));
   a.inv_bc2 = (float)(1.0 / (1.0 - std::pow((double)b2, c)));
+  a.bc_dev = nullptr;
+  if (count_dev) {
+    mfac::adamw_bias_correction_kernel<<<1, 1, 0, s>>>(count_dev, scratch_dev, b1, b2);
+    mfac::count_launch();
+    a.bc_dev = scratch_dev;
+  }
   const int64_t threads = mfac::ceil_div<int64_t>(d.total, 4);
   // 16 B read + 12 B write per parameter, + 2 B bf16 shadow
-  void* prof = mfac::profile_begin(MFAC_PROF_ADAMW, (shadow ? 30.0 : 28.0) * (double)d.total, (cudaStream_t)stream);
-  mfac::adamw_kernel<<<(unsigned)mfac::ceil_div<int64_t>(threads, 256), 256, 0, (cudaStream_t)stream>>>(a, d);
-  mfac::profile_end(prof, (cudaStream_t)stream);
+  void* prof = mfac::profile_begin(MFAC_PROF_ADAMW, (shadow ? 30.0 : 28.0) * (double)d.total, s);
+  mfac::adamw_kernel<<<(unsigned)mfac::ceil_div<int64_t>(threads, 256), 256, 0, s>>>(a, d);
+  mfac::profile_end(prof, s);
   mfac::count_launch();
   return mfac::launch_status();
+}
+}  // namespace
+
+int mfac_adamw_step(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
+                    int64_t count, float lr, float b1, float b2, float eps, float weight_decay, float grad_scale,
+                    void* stream) {
+  return adamw_launch(dims, params, grads, mu, nu, shadow, count, nullptr, nullptr, lr, b1, b2, eps, weight_decay, grad_scale,
+                      stream);
+}
+
+int mfac_adamw_step_dev(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow,
+                        uint64_t* count_dev, float* scratch_dev, float lr, float b1, float b2, float eps, float weight_decay,
+                        float grad_scale, void* stream) {
+  if (!count_dev || !scratch_dev) return MFAC_ERR_NULL;
+  return adamw_launch(dims, params, grads, mu, nu, shadow, 0, count_dev, scratch_dev, lr, b1, b2, eps, weight_decay, grad_scale,
+                      stream);
 }
 
 }  // extern "C"

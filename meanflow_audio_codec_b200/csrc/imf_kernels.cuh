@@ -98,6 +98,7 @@ struct PrepArgs {
 
 __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims d) {
   const int64_t b = blockIdx.x;
+  const uint64_t step = a.cfg.step_dev ? *a.cfg.step_dev : a.cfg.step;
   __shared__ float s_tr[2];
   if (threadIdx.x == 0) {
     float t, r;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
       t = a.t_in[b];
       r = a.r_in[b];
     } else {
-      const float4 n4 = philox_normal4(a.cfg.row_offset + b, 1u, a.cfg.seed, a.cfg.step);
+      const float4 n4 = philox_normal4(a.cfg.row_offset + b, 1u, a.cfg.seed, step);
       const float lt = 1.0f / (1.0f + expf(-(n4.x * a.cfg.time_std + a.cfg.time_mean)));
       const float lr = 1.0f / (1.0f + expf(-(n4.y * a.cfg.time_std + a.cfg.time_mean)));
       t = fmaxf(lt, lr);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
     float ev[4] = {0.f, 0.f, 0.f, 0.f};
     if (!a.e_in && j4 < d.D) {
       const uint64_t idx = ((a.cfg.row_offset + (uint64_t)b) * (uint64_t)d.Dp + (uint64_t)j4) >> 2;
-      const float4 n4 = philox_normal4(idx, 0u, a.cfg.seed, a.cfg.step);
+      const float4 n4 = philox_normal4(idx, 0u, a.cfg.seed, step);
       ev[0] = n4.x; ev[1] = n4.y; ev[2] = n4.z; ev[3] = n4.w;
     }
 #pragma unroll

@@ -1,0 +1,66 @@
+"""CUDA-graph capture of the training step -- this build's counterpart of wrapping the reference's ``train_step``
+in ``jax.jit`` (the reference leaves it un-jitted).
+
+    step = GraphedTrainStep(state, loss_strategy, tokenization, example_batch)
+    loss = step(batch)            # batch: CUDA tensor with the example's shape; loss: 0-d CUDA tensor (static buffer)
+
+One replay = tokenise + iMF loss/grad + AdamW (+ bf16 shadow refresh): ~265 kernel launches submitted as ONE graph
+launch, which is what matters at the config-faithful batch of 128 where the step is launch-bound.  The step counter
+(RNG stream offset, AdamW bias correction) lives in device memory and advances inside the graph, so consecutive
+replays draw fresh (e, t, r) exactly like consecutive eager steps with ``step=state.step``.
+ref: trainers/training_steps.py:15-61, trainers/train.py:333-347.
+"""
+from __future__ import annotations
+
+import torch
+
+from .loss_strategies import LossStrategy
+from .mlp_flow import TrainState
+
+
+class GraphedTrainStep:
+    def __init__(self, state: TrainState, loss_strategy: LossStrategy, tokenization, example: torch.Tensor, key: int = 0,
+                 warmup: int = 2):
+        if not example.is_cuda:
+            raise ValueError("example batch must be a CUDA tensor")
+        self.state, self.strategy, self.tok, self.key = state, loss_strategy, tokenization, key
+        dev = example.device
+        self.x = example.clone()
+        self.count = torch.full((), int(state.opt_state["count"]), dtype=torch.int64, device=dev)   # read as uint64 by libmfac
+        self.scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.steps_run = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up outside capture: table uploads, workspace allocation, attributes
+            snap = [t.clone() for t in (self._flat(), state.opt_state["mu"], state.opt_state["nu"], self.count)]
+            for _ in range(warmup):
+                self._body()
+            for t, s in zip((self._flat(), state.opt_state["mu"], state.opt_state["nu"], self.count), snap):
+                t.copy_(s)                        # warm-up must not advance training
+            self.state.model.flat_params(self.state.params).shadow()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _flat(self):
+        return self.state.model.flat_params(self.state.params).flat
+
+    def _body(self):
+        x = self.x
+        if self.tok is not None:
+            x = self.tok.tokenize(x)
+            x = x.reshape(x.shape[0], -1)
+        loss, grads = self.strategy.compute_loss(self.state, self.key, x, step_tensor=self.count)
+        self.state.apply_gradients(grads=grads, count_tensor=self.count, scratch=self.scratch)
+        return loss
+
+    def __call__(self, batch: torch.Tensor) -> torch.Tensor:
+        if batch.data_ptr() != self.x.data_ptr():
+            self.x.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        self.steps_run += 1
+        self.state.step += 1
+        self.state.opt_state["count"] += 1
+        return self.loss

@@ -66,13 +66,15 @@ class ImprovedMeanFlowLoss(LossStrategy):
         self.use_weighted_loss = use_weighted_loss
         self.last_aux = None
 
-    def _config(self, seed: int, step: int, row_offset: int) -> _lib.ImfConfig:
+    def _config(self, seed: int, step: int, row_offset: int, step_dev=None) -> _lib.ImfConfig:
         ns, ts = self.noise_schedule, self.time_sampling
         return _lib.ImfConfig(ns.noise_min, ns.noise_max, ts.mean, ts.std, ts.data_proportion, 1e-3,
-                              1 if self.use_weighted_loss else 0, int(seed) & (2 ** 64 - 1), int(step), int(row_offset))
+                              1 if self.use_weighted_loss else 0, int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
+                              None if step_dev is None else step_dev.data_ptr())
 
     def compute_loss(self, state: TrainState, key, x, *, noise=None, t=None, r=None, step: int | None = None,
-                     row_offset: int = 0, return_aux: bool = False):
+                     row_offset: int = 0, return_aux: bool = False, step_tensor=None):
+        """``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay)."""
         model: ConditionalFlow = state.model
         fp = model.flat_params(state.params)
         x = _lib.require_cuda(x, "x").to(torch.float32).contiguous()
@@ -99,7 +101,7 @@ class ImprovedMeanFlowLoss(LossStrategy):
             aux_t.update({k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("per_example", "t", "r")})
             aux = _lib.ImfAux(*[aux_t[k].data_ptr() for k in ("v", "u", "dudt", "per_example", "e", "t", "r")])
         cfg = self._config(int(key) if not isinstance(key, torch.Tensor) else int(key.sum()), state.step if step is None else step,
-                           row_offset)
+                           row_offset, step_tensor)
         ws = model.workspace(_lib.WS_LOSS_GRAD, B, dev)
         ptr = lambda a: None if a is None else a.data_ptr()  # noqa: E731
         with torch.cuda.device(dev):

@@ -237,12 +237,23 @@ class TrainState:
         opt_state = {"count": 0, "mu": torch.zeros_like(fp.flat), "nu": torch.zeros_like(fp.flat)}
         return cls(0, apply_fn, fp.tree(), tx, opt_state, model)
 
-    def apply_gradients(self, *, grads, grad_scale: float = 1.0):
+    def apply_gradients(self, *, grads, grad_scale: float = 1.0, count_tensor=None, scratch=None):
         """AdamW update in place on the flat buffers (one fused kernel that also refreshes the bf16
-        shadow); returns the advanced state like the reference's functional API."""
+        shadow); returns the advanced state like the reference's functional API.
+        ``count_tensor`` (uint64 CUDA scalar) + ``scratch`` (2 fp32) select the graph-capturable form whose step
+        count lives, and is advanced, on the device."""
         fp = self.model.flat_params(self.params)
         g = grads.flat if isinstance(grads, ParamTree) else self.model.flat_params(grads).flat
         tx = self.tx
+        if count_tensor is not None:
+            with torch.cuda.device(fp.flat.device):
+                _lib.check(_lib.lib().mfac_adamw_step_dev(C.byref(self.model.dims), fp.flat.data_ptr(), g.data_ptr(),
+                                                          self.opt_state["mu"].data_ptr(), self.opt_state["nu"].data_ptr(),
+                                                          fp.shadow().data_ptr(), count_tensor.data_ptr(), scratch.data_ptr(),
+                                                          tx.learning_rate, tx.b1, tx.b2, tx.eps, tx.weight_decay,
+                                                          float(grad_scale), _lib.stream_ptr()), "adamw_step_dev")
+            fp.mark_shadow_current()
+            return self
         with torch.cuda.device(fp.flat.device):
             _lib.check(_lib.lib().mfac_adamw_step(C.byref(self.model.dims), fp.flat.data_ptr(), g.data_ptr(),
                                                   self.opt_state["mu"].data_ptr(), self.opt_state["nu"].data_ptr(),

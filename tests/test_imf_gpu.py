@@ -159,3 +159,38 @@ def test_internal_rng_statistics(cuda):
     assert (r[: B // 2] == t[: B // 2]).all() and (r[B // 2:] < t[B // 2:]).mean() > 0.95
     # logit-normal(-0.4, 1): median of max(t1,t2) sits above sigmoid(-0.4)
     assert 0.35 < np.median(np.minimum(t, 1)) < 0.75
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """GraphedTrainStep (one CUDA-graph replay per step, device-side step counter) == eager train_step with step=state.step:
+    same Philox draws, same AdamW bias correction; only the split-K atomics' summation order differs."""
+    import meanflow_audio_codec_b200 as m
+    D_raw, B = 784, 64
+    tok = m.MDCTTokenization(window_size=512, hop_size=256)
+    model = m.ConditionalFlow(noise_dimension=1024, condition_dimension=32, num_blocks=2, latent_dimension=64)
+    strat = m.ImprovedMeanFlowLoss()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    batches = [0.1 * torch.randn(B, D_raw, device="cuda", generator=g) for _ in range(3)]
+
+    def fresh():
+        params = model.init(11)["params"]
+        return m.TrainState.create(apply_fn=model.apply, params=params, tx=m.adamw(1e-3, 1e-4))
+
+    s_e = fresh()
+    losses_e = []
+    for xb in batches:
+        x = tok.tokenize(xb).reshape(B, -1)
+        s_e, loss, _ = m.train_step(s_e, 0, x, strat)
+        losses_e.append(float(loss))
+    flat_e = model.flat_params(s_e.params).flat.clone()
+
+    s_g = fresh()
+    step = m.GraphedTrainStep(s_g, strat, tok, batches[0], key=0)
+    losses_g = [float(step(xb)) for xb in batches]
+    flat_g = model.flat_params(s_g.params).flat
+    assert s_g.step == 3 and int(step.count) == 3
+    assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-5
+    rel = float((flat_g - flat_e).norm() / flat_e.norm())
+    assert rel < 1e-5, rel
+    # the update actually moved the weights
+    assert float((flat_g - model.init(11)["params"].flat).norm()) > 0
