@@ -133,12 +133,10 @@ int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_
   return MFAC_SUCCESS;
 }
 
-int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* partial, float* out, int kind, int limit, const Dims& d,
+int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* /*partial*/, float* out, int kind, int limit, const Dims& d,
            cudaStream_t s) {
   const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
-  colsum_partial_vec_kernel<<<dim3(ceil_div(ld, 256), R), 256, 0, s>>>(G, ld, B, partial);
-  count_launch();
-  colsum_final_kernel<<<blocks_for(ld, 128), 128, 0, s>>>(partial, ld, R, out, kind, limit, d);
+  colsum_atomic_vec_kernel<<<dim3(ceil_div(ld, 256), R), 256, 0, s>>>(G, ld, B, out, kind, limit, d);
   count_launch();
   return launch_status();
 }
@@ -166,7 +164,7 @@ struct LossGradPlan {
   __nv_bfloat16 *gcd, *md, *hind, *gd;
   float* xd;
   // loss / backward
-  float *row_loss, *g_x, *g_lat, *g_hin, *partial;
+  float *row_loss, *g_x, *g_lat, *partial;
   __nv_bfloat16 *g_o, *g_a, *g_m, *g_ac, *g_latb, *g_ae;
 
   void plan(Arena& ar, const Dims& d, int64_t B) {
@@ -204,7 +202,6 @@ struct LossGradPlan {
     row_loss = ar.take<float>(B);
     g_x = ar.take<float>(B * d.Dp);
     g_lat = ar.take<float>(B * d.Lp);
-    g_hin = ar.take<float>(B * d.Ip);
     partial = ar.take<float>(ceil_div<int64_t>(B, COLSUM_VROWS) * d.Mp);
     g_o = ar.take<__nv_bfloat16>(B * d.Dp);
     g_a = ar.take<__nv_bfloat16>(B * d.Ip);
@@ -388,8 +385,9 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
     MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
     MFAC_OK(colsum(p.g_a, d.Ip, B, p.partial, gk + d.o_m1b, MAP_CM, 0, d, s));
-    MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearF32{nullptr, p.g_hin, d.Ip}, s));
-    LnBwdArgs lb{p.g_hin, p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
+    // g_hin = g_a W1^T goes out in bf16 straight into g_m[:, Ip:2Ip]: it IS the shift gradient (hin = (1+s1) n + shift)
+    MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
+    LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
     MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));

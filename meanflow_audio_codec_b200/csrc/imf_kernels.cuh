@@ -319,12 +319,12 @@ __global__ void bwd_block_out_kernel(const float* g_x, const __nv_bfloat16* m, c
 
 // LayerNorm / modulation backward, one block per row.
 struct LnBwdArgs {
-  const float* g_hin;       // [B, Ip]
+  // g_hin (= g_shift) arrives in bf16, already sitting in its final place g_m[:, Ip:2Ip] (written by the dX GEMM epilogue)
   const float* lat;         // [B, Lp]
   const float* x;           // [B, Dp]  block input
   const float *mu, *rstd;   // [B]
   const __nv_bfloat16* m;   // [B, Mp]
-  __nv_bfloat16* g_m;       // [B, Mp]  writes [0, 2Ip)
+  __nv_bfloat16* g_m;       // [B, Mp]  reads [Ip, 2Ip), writes [0, Ip)
   float* g_lat;             // [B, Lp]  +=
   float* g_x;               // [B, Dp]  +=
 };
@@ -342,15 +342,14 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a, Dims d
     if (real) {
       const float c = p < d.Lp ? a.lat[b * d.Lp + p] : a.x[b * d.Dp + (p - d.Lp)];
       n = (c - mu) * rstd;
-      gh = a.g_hin[b * d.Ip + p];
+      gh = __bfloat162float(a.g_m[b * d.Mp + d.Ip + p]);
       gn = gh * (1.0f + __bfloat162float(a.m[b * d.Mp + p]));
     }
     s_n[p] = n;
     s_gn[p] = gn;
     s1sum += gn;
     s2sum += gn * n;
-    a.g_m[b * d.Mp + p] = __float2bfloat16(gh * n);          // g_s1
-    a.g_m[b * d.Mp + d.Ip + p] = __float2bfloat16(gh);       // g_shift
+    a.g_m[b * d.Mp + p] = __float2bfloat16(gh * n);          // g_s1  (g_shift = g_hin is already in place)
   }
   const float inv_i = 1.0f / (float)d.I;
   const float m1 = block_sum(s1sum, red) * inv_i;
@@ -541,7 +540,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
     float c[8], gh[8], s1[8], gs1[8];
     if (col < d.Lp) ld8_f32(a.lat + b * d.Lp + col, c);
     else ld8_f32(a.x + b * d.Dp + (col - d.Lp), c);
-    ld8_f32(a.g_hin + b * d.Ip + col, gh);
+    ld8_bf16(a.g_m + b * d.Mp + d.Ip + col, gh);
     ld8_bf16(a.m + b * d.Mp + col, s1);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -552,7 +551,6 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
       s2sum += gn[i][q] * n[i][q];
     }
     st8_bf16(a.g_m + b * d.Mp + col, gs1);
-    st8_bf16(a.g_m + b * d.Mp + d.Ip + col, gh);
   }
   const float inv_i = 1.0f / (float)d.I;
   const float m1 = warp_sum(s1sum) * inv_i, m2 = warp_sum(s2sum) * inv_i;
@@ -589,9 +587,12 @@ __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x
   st8_bf16(g_m + b * d.Mp + 2 * d.Ip + j, gs2);
 }
 
-// Column sums, stage 1, vectorised: grid (ceil(ld/256), R); thread = 8 columns x every 8th row of a 256-row slab.
+// Column sums (bias gradients), one pass: grid (ceil(ld/256), R); thread = 8 columns x every 8th row of a 256-row slab;
+// the slab's sums are added to out[map(col)] with red.global.add (out is zeroed with the rest of the gradient, like the
+// split-K weight gradients it sits next to).
 constexpr int COLSUM_VROWS = 256;
-__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* partial) {
+__global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* out, int kind,
+                                                                int limit, Dims d) {
   __shared__ float s_red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -609,12 +610,13 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const __nv_bflo
 #pragma unroll
   for (int q = 0; q < 8; ++q) s_red[rl][cg * 8 + q] = acc[q];
   __syncthreads();
-  const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < ld) {
-    float s = 0.f;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < ld) {
+    float sum = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += s_red[q][c];
-    partial[(int64_t)blockIdx.y * ld + blockIdx.x * 256 + c] = s;
+    for (int q = 0; q < 8; ++q) sum += s_red[q][threadIdx.x];
+    const int oc = map_col(kind, c, limit, d);
+    if (oc >= 0) atomicAdd(out + oc, sum);
   }
 }
 
