@@ -134,9 +134,10 @@ int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_
 }
 
 int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* /*partial*/, float* out, int kind, int limit, const Dims& d,
-           cudaStream_t s) {
+           cudaStream_t s, int ncols = 0) {
+  if (ncols == 0) ncols = ld;
   const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
-  colsum_atomic_vec_kernel<<<dim3(ceil_div(ld, 256), R), 256, 0, s>>>(G, ld, B, out, kind, limit, d);
+  colsum_atomic_vec_kernel<<<dim3(ceil_div(ncols, 256), R), 256, 0, s>>>(G, ld, ncols, B, out, kind, limit, d);
   count_launch();
   return launch_status();
 }
@@ -378,10 +379,11 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     SavedBlock& sb = p.blk[k];
     float* gk = grads + (int64_t)k * d.blk_stride;
     const float* x_in = p.xs + (int64_t)k * B * d.Dp;
-    bwd_block_out_vec_kernel<<<blocks_for(B * d.Dp / 8, 256), 256, 0, s>>>(p.g_x, sb.m, sb.o, p.g_o, p.g_m, d, B);
+    // g_o, g_s2 and both of their bias-gradient column sums (db2, the s2 third of dbc2) in one pass
+    bwd_block_out_vec_kernel<<<dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), 256, 0, s>>>(
+        p.g_x, sb.m, sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B);
     count_launch();
     MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
-    MFAC_OK(colsum(p.g_o, d.Dp, B, p.partial, gk + d.o_m2b, MAP_ID, d.D, d, s));
     MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
     MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
     MFAC_OK(colsum(p.g_a, d.Ip, B, p.partial, gk + d.o_m1b, MAP_CM, 0, d, s));
@@ -391,7 +393,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     MFAC_OK(ln_bwd(lb, d, B, s));
     MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
-    MFAC_OK(colsum(p.g_m, d.Mp, B, p.partial, gk + d.o_c2b, MAP_MM, 0, d, s));
+    MFAC_OK(colsum(p.g_m, d.Mp, B, p.partial, gk + d.o_c2b, MAP_MM, 0, d, s, 2 * d.Ip));  // s1 | shift thirds
     MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
     MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, 1, d}, s));
     MFAC_OK(colsum(p.g_ac, d.Cp, B, p.partial, gk + d.o_c1b, MAP_ID, d.C, d, s));

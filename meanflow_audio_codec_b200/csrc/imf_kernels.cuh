@@ -303,20 +303,6 @@ __global__ void __launch_bounds__(1024) sum_rows_kernel(const float* v, int64_t 
 // ---------------------------------------------------------------------------------------
 // backward elementwise pieces
 // ---------------------------------------------------------------------------------------
-// g_o = g_x (1+s2)/nb  (bf16, GEMM operand);  g_s2 = g_x o / nb -> g_m[:, 2Ip:]
-__global__ void bwd_block_out_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o, __nv_bfloat16* g_o,
-                                     __nv_bfloat16* g_m, Dims d, int64_t B) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * d.Dp) return;
-  const int64_t b = i / d.Dp;
-  const int j = (int)(i % d.Dp);
-  const float inv_nb = 1.0f / (float)d.nb;
-  const float g = g_x[i];
-  const float s2 = __bfloat162float(m[b * d.Mp + 2 * d.Ip + j]);
-  g_o[i] = __float2bfloat16(g * (1.0f + s2) * inv_nb);
-  g_m[b * d.Mp + 2 * d.Ip + j] = __float2bfloat16(g * __bfloat162float(o[i]) * inv_nb);
-}
-
 // LayerNorm / modulation backward, one block per row.
 struct LnBwdArgs {
   // g_hin (= g_shift) arrives in bf16, already sitting in its final place g_m[:, Ip:2Ip] (written by the dX GEMM epilogue)
@@ -368,47 +354,14 @@ __global__ void f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t
   if (i < n) dst[i] = __float2bfloat16(src[i]);
 }
 
-// Column sums of a bf16 [B, ld] matrix, deterministic two-stage.
-// stage 1: grid (ld/64, R) blocks of 256 threads; partial[r][ld]
-constexpr int COLSUM_ROWS = 512;
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* partial) {
-  __shared__ float2 s_red[8][32];
-  const int cpair = threadIdx.x & 31, rlane = threadIdx.x >> 5;
-  const int col = blockIdx.x * 64 + cpair * 2;
-  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_ROWS;
-  const int64_t r1 = min(B, r0 + COLSUM_ROWS);
-  float2 acc = make_float2(0.f, 0.f);
-  for (int64_t r = r0 + rlane; r < r1; r += 8) {
-    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(G + r * ld + col));
-    acc.x += v.x;
-    acc.y += v.y;
-  }
-  s_red[rlane][cpair] = acc;
-  __syncthreads();
-  if (rlane == 0) {
-#pragma unroll
-    for (int q = 1; q < 8; ++q) { acc.x += s_red[q][cpair].x; acc.y += s_red[q][cpair].y; }
-    partial[(int64_t)blockIdx.y * ld + col] = acc.x;
-    partial[(int64_t)blockIdx.y * ld + col + 1] = acc.y;
-  }
-}
-// stage 2: out[map(col)] = sum_r partial[r][col]; kind selects the padded->real column map
+// padded -> real column maps of the flat (Flax-order) gradient
+constexpr int COLSUM_VROWS = 256;
 enum ColMap { MAP_ID = 0, MAP_CM = 1, MAP_MM = 2 };
 __device__ __forceinline__ int map_col(int kind, int p, int limit, const Dims& d) {
   if (kind == MAP_CM) return d.cm_inv(p);
   if (kind == MAP_MM) return d.mm_inv(p);
   return p < limit ? p : -1;
 }
-__global__ void colsum_final_kernel(const float* partial, int ld, int R, float* out, int kind, int limit, Dims d) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ld) return;
-  const int c = map_col(kind, p, limit, d);
-  if (c < 0) return;
-  float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[(int64_t)r * ld + p];
-  out[c] = s;
-}
-
 // ---------------------------------------------------------------------------------------
 // sampler elementwise updates on padded [B, Dp] fp32 buffers
 // ---------------------------------------------------------------------------------------
@@ -566,40 +519,65 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
   }
 }
 
-// 8 elements per thread; Dp is a multiple of 64 so a vector never straddles a row
+// Backward of the block output, fused with the two bias-gradient column sums that read its results:
+//   g_o = g_x (1+s2)/nb -> bf16 (GEMM operand), db2 += colsum(g_o);  g_s2 = g_x o / nb -> g_m[:, 2Ip:], dbc2[s2 part] += colsum.
+// grid (Dp/256, ceil(B/256)); thread = 8 columns x every 8th row of a 256-row slab (same shape as the column-sum kernel).
 __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o,
-                                                                __nv_bfloat16* g_o, __nv_bfloat16* g_m, Dims d, int64_t B) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i >= B * d.Dp) return;
-  const int64_t b = i / d.Dp;
-  const int j = (int)(i % d.Dp);
+                                                                __nv_bfloat16* g_o, __nv_bfloat16* g_m, float* db_o, float* db_m,
+                                                                Dims d, int64_t B) {
+  __shared__ float s_red[2][8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_VROWS;
+  const int64_t r1 = min(B, r0 + COLSUM_VROWS);
   const float inv_nb = 1.0f / (float)d.nb;
-  float g[8], s2[8], ov[8], go[8], gs2[8];
-  ld8_f32(g_x + i, g);
-  ld8_bf16(m + b * d.Mp + 2 * d.Ip + j, s2);
-  ld8_bf16(o + i, ov);
+  float so[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < d.Dp) {
+#pragma unroll 2
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float g[8], s2[8], ov[8], go[8], gs2[8];
+      ld8_f32(g_x + r * d.Dp + col, g);
+      ld8_bf16(m + r * d.Mp + 2 * d.Ip + col, s2);
+      ld8_bf16(o + r * d.Dp + col, ov);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    go[q] = g[q] * (1.0f + s2[q]) * inv_nb;
-    gs2[q] = g[q] * ov[q] * inv_nb;
+      for (int q = 0; q < 8; ++q) {
+        go[q] = g[q] * (1.0f + s2[q]) * inv_nb;
+        gs2[q] = g[q] * ov[q] * inv_nb;
+        so[q] += go[q];
+        ss[q] += gs2[q];
+      }
+      st8_bf16(g_o + r * d.Dp + col, go);
+      st8_bf16(g_m + r * d.Mp + 2 * d.Ip + col, gs2);
+    }
   }
-  st8_bf16(g_o + i, go);
-  st8_bf16(g_m + b * d.Mp + 2 * d.Ip + j, gs2);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { s_red[0][rl][cg * 8 + q] = so[q]; s_red[1][rl][cg * 8 + q] = ss[q]; }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < d.Dp) {
+    float a = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { a += s_red[0][q][threadIdx.x]; b2 += s_red[1][q][threadIdx.x]; }
+    const int co = map_col(MAP_ID, c, d.D, d);
+    if (co >= 0) atomicAdd(db_o + co, a);
+    const int cm = map_col(MAP_MM, 2 * d.Ip + c, 0, d);
+    if (cm >= 0) atomicAdd(db_m + cm, b2);
+  }
 }
 
 // Column sums (bias gradients), one pass: grid (ceil(ld/256), R); thread = 8 columns x every 8th row of a 256-row slab;
 // the slab's sums are added to out[map(col)] with red.global.add (out is zeroed with the rest of the gradient, like the
 // split-K weight gradients it sits next to).
-constexpr int COLSUM_VROWS = 256;
-__global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloat16* G, int ld, int64_t B, float* out, int kind,
-                                                                int limit, Dims d) {
+__global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloat16* G, int ld, int ncols, int64_t B, float* out,
+                                                                int kind, int limit, Dims d) {
   __shared__ float s_red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   const int64_t r0 = (int64_t)blockIdx.y * COLSUM_VROWS;
   const int64_t r1 = min(B, r0 + COLSUM_VROWS);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (col < ld) {
+  if (col < ncols) {
+#pragma unroll 2
     for (int64_t r = r0 + rl; r < r1; r += 8) {
       float v[8];
       ld8_bf16(G + r * ld + col, v);
@@ -611,7 +589,7 @@ __global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloa
   for (int q = 0; q < 8; ++q) s_red[rl][cg * 8 + q] = acc[q];
   __syncthreads();
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < ld) {
+  if (c < ncols) {
     float sum = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) sum += s_red[q][threadIdx.x];
