@@ -19,6 +19,7 @@
 #include <mutex>
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 
 #include "mfac_common.cuh"
 
@@ -62,6 +63,7 @@ struct TableSet {
 
 std::mutex g_mu;
 std::map<std::pair<int, int>, TableSet> g_tables;  // (device, N)
+bool g_imdct_gather = getenv("MFAC_IMDCT_GATHER") != nullptr;  // debug: force the shared-memory gather kernel
 
 template <typename T>
 int upload(const std::vector<T>& h, const T** out) {
@@ -627,6 +629,113 @@ imdct512h256_kernel(const float* __restrict__ X, float* __restrict__ y, FftTable
   }
 }
 
+// ------------------------------------------------------------------ inverse, streaming overlap-add in registers
+// A half-warp walks along consecutive frames of one clip.  After the DCT-IV of frame i, lane ln holds v_i[p] at the 32
+// positions p = 2 ln + e + 32 k2.  Each v_i[p] lands on exactly two output samples, and both belong either to this lane
+// or to its mirror lane 15 - ln:
+//     p >= 256:  block i   at r = p - 256  (+w[p-256])      block i+1 at r = 511 - p  (-w[767-p], mirror lane)
+//     p <  256:  block i+3 at r = p        (-w[768+p])      block i+2 at r = 255 - p  (-w[767-p], mirror lane)
+// so the overlap-add is three 16-value register accumulators per lane (blocks i+1..i+3) and one lane-mirror shuffle
+// per value; block i is complete after frame i and leaves as eight 128-byte lines per half-warp.  No shared-memory
+// frame store, no gather pass, no CTA barrier; a stream re-does 3 halo frames.  Shared memory holds only the exchange
+// buffers and the per-lane constant tables (pre/post twiddles, window products).
+constexpr int S2_TABLE_F2 = 256 + 256 + 128 + 128 + 256;   // pre | post | Wl_hi | Wl_lo | Wm   (float2 each)
+
+__global__ void __launch_bounds__(F2_THREADS, 3)
+imdct512h256_stream_kernel(const float* __restrict__ X, float* __restrict__ y, FftTables tab, int64_t nf, int64_t X_clip_stride,
+                           int64_t y_clip_stride, int S, int streams_per_clip, int64_t total_streams) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float2* sEx = reinterpret_cast<float2*>(smem_raw);
+  float2* sPre = sEx + (F2_THREADS / 16) * F2_EX;   // [j][ln]   pre[16 j + ln]
+  float2* sPost = sPre + 256;                       // [k2][ln]  post[ln + 16 k2] * 2/N
+  float2* sWhi = sPost + 256;                       // [kk][ln]  { w[r], w[r+1] },               r = 2 ln + 32 kk
+  float2* sWlo = sWhi + 128;                        // [kk][ln]  {-w[768+r], -w[769+r]}
+  float2* sWm = sWlo + 128;                         // [k2][ln]  {-w[767-p], -w[766-p]},         p = 2 ln + 32 k2
+  const int tid = threadIdx.x, ln = tid & 15, hw = tid >> 4;
+  for (int i = tid; i < 256; i += F2_THREADS) {
+    const int l = i & 15, k = i >> 4;
+    sPre[i] = tab.pre[16 * k + l];
+    const float2 po = tab.post[l + 16 * k];
+    sPost[i] = make_float2(po.x * (2.0f / FFT_N), po.y * (2.0f / FFT_N));
+    const int p = 2 * l + 32 * k;
+    sWm[i] = make_float2(-tab.window[767 - p], -tab.window[766 - p]);
+    if (k < 8) {
+      sWhi[i] = make_float2(tab.window[p], tab.window[p + 1]);
+      sWlo[i] = make_float2(-tab.window[768 + p], -tab.window[769 + p]);
+    }
+  }
+  float2 tw[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tw[j] = tab.w256[(ln * j) & 255];
+  __syncthreads();
+
+  const int64_t sid = (int64_t)blockIdx.x * (F2_THREADS / 16) + hw;
+  const bool valid = sid < total_streams;
+  const int64_t sidc = valid ? sid : total_streams - 1;      // idle half-warps shadow a real stream (no stores)
+  const int64_t b = sidc / streams_per_clip;
+  const int64_t i0 = (sidc % streams_per_clip) * (int64_t)S;
+  const int64_t nblocks = nf + 3;
+  const float* Xb = X + b * X_clip_stride;
+  float* yb = y + b * y_clip_stride;
+  float2* ex = sEx + hw * F2_EX;
+
+  float2 accA[8], accB[8], accC[8];                          // partial blocks i, i+1, i+2 (float2 over e)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accA[k] = accB[k] = accC[k] = make_float2(0.f, 0.f);
+
+  auto load_frame = [&](int64_t fi, float2 (&in)[16]) {
+    const bool ok = fi >= 0 && fi < nf;
+    const float2* src = reinterpret_cast<const float2*>(Xb + (ok ? fi : 0) * FFT_N) + ln;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) in[j] = ok ? __ldg(src + 16 * j) : make_float2(0.f, 0.f);
+  };
+  float2 in[16];
+  load_frame(i0 - 3, in);
+
+#pragma unroll 1
+  for (int j = 0; j < S + 3; ++j) {
+    const int64_t fi = i0 - 3 + j;
+    float2 c[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float hi = __shfl_xor_sync(0xffffffffu, in[15 - q].y, 15);   // X[511 - 2m]
+      c[q] = cmul(make_float2(in[q].x, hi), sPre[16 * q + ln]);
+    }
+    load_frame(fi + 1, in);                                              // flies during this frame's FFT
+    fft256_lanes16(c, tw, ex, PostSmem{sPost + ln}, ln);
+    // v[k2] = { v_i[2 ln + 32 k2], v_i[2 ln + 32 k2 + 1] }
+    float2 v[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
+      v[k2] = make_float2(c[fidx(k2)].x, -im);
+    }
+    // block i is complete: t = 0 term of this frame on top of accA
+    if (valid && j >= 3 && fi < nblocks) {
+      float2* dst = reinterpret_cast<float2*>(yb + fi * 256) + ln;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const float2 w = sWhi[16 * kk + ln];
+        dst[16 * kk] = make_float2(fmaf(w.x, v[kk + 8].x, accA[kk].x), fmaf(w.y, v[kk + 8].y, accA[kk].y));
+      }
+    }
+    // mirror terms u[k2] = -w[767 - p] v[p]; the value for (kk, e) comes from the mirror lane's (15 - kk | 7 - kk, 1 - e)
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const float2 wm1 = sWm[16 * (15 - kk) + ln], wm2 = sWm[16 * (7 - kk) + ln], wl = sWlo[16 * kk + ln];
+      const float u1x = __shfl_xor_sync(0xffffffffu, wm1.y * v[15 - kk].y, 15);   // -> e' = 0 of block i+1
+      const float u1y = __shfl_xor_sync(0xffffffffu, wm1.x * v[15 - kk].x, 15);   // -> e' = 1
+      const float u2x = __shfl_xor_sync(0xffffffffu, wm2.y * v[7 - kk].y, 15);    // -> block i+2
+      const float u2y = __shfl_xor_sync(0xffffffffu, wm2.x * v[7 - kk].x, 15);
+      accA[kk] = make_float2(accB[kk].x + u1x, accB[kk].y + u1y);
+      accB[kk] = make_float2(accC[kk].x + u2x, accC[kk].y + u2y);
+      accC[kk] = make_float2(wl.x * v[kk].x, wl.y * v[kk].y);                     // t = 3 term opens block i+3
+    }
+  }
+}
+
+constexpr int S2_SMEM = ((F2_THREADS / 16) * F2_EX + S2_TABLE_F2) * 8;
+
 constexpr int F2_SMEM = 2 * F2_SEG_WORDS * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
 constexpr int I2_SMEM = I2_FRAMES * FFT_N * 4 + (F2_THREADS / 16) * F2_EX * 8;
 
@@ -764,9 +873,27 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
       MFAC_CUDA_OK(cudaFuncSetAttribute(imdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM));
       configured2 = true;
     }
-    dim3 grid((unsigned)ceil_div<int64_t>(nf + 3, I2_BLOCKS), (unsigned)B);
     void* prof = profile_begin(MFAC_PROF_IMDCT, 4.0 * (double)B * ((double)L + (double)nf * N), stream);
-    imdct512h256_kernel<<<grid, F2_THREADS, I2_SMEM, stream>>>(X, y, ts.fft, nf, L, io.in_clip_stride, io.out_clip_stride);
+    const int64_t nblocks = nf + 3;
+    if (nblocks >= 16 && (io.out_clip_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 && !g_imdct_gather) {
+      // stream length S: whole waves of (SMs x 3 CTAs x 8 streams) with the 3-frame halo charged to every stream
+      const double slots = (double)num_sms() * 3 * (F2_THREADS / 16);
+      int best_S = 32;
+      double best = -1.0;
+      for (int S = 16; S <= 96; ++S) {
+        const double streams = (double)B * (double)ceil_div<int64_t>(nblocks, S);
+        const double waves = streams / slots;
+        const double eff = (waves / std::ceil(waves)) * ((double)S / (S + 3));
+        if (eff > best + 1e-9) { best = eff; best_S = S; }
+      }
+      const int spc = (int)ceil_div<int64_t>(nblocks, best_S);
+      const int64_t total = B * (int64_t)spc;
+      imdct512h256_stream_kernel<<<(unsigned)ceil_div<int64_t>(total, F2_THREADS / 16), F2_THREADS, S2_SMEM, stream>>>(
+          X, y, ts.fft, nf, io.in_clip_stride, io.out_clip_stride, best_S, spc, total);
+    } else {
+      dim3 grid((unsigned)ceil_div<int64_t>(nf + 3, I2_BLOCKS), (unsigned)B);
+      imdct512h256_kernel<<<grid, F2_THREADS, I2_SMEM, stream>>>(X, y, ts.fft, nf, L, io.in_clip_stride, io.out_clip_stride);
+    }
     profile_end(prof, stream);
     count_launch();
     return launch_status();
