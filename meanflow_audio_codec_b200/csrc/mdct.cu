@@ -424,6 +424,39 @@ struct PostRegs {   // post twiddles in registers
   __device__ __forceinline__ float2 operator()(int k2) const { return v[k2]; }
 };
 
+// fold + window + pre-twiddle of one frame whose even / odd sample planes start at E / O (constants folded into kf):
+// plane index r -> r + 16 (r >> 7); a 16-lane group never straddles a 128-word block
+__device__ __forceinline__ void fold_frame(const float* E, const float* O, const float (&kf)[16][4], float2 (&c)[16], int ln) {
+#define MFAC_SK(r) ((r) + 16 * ((r) >> 7))
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = O[MFAC_SK(383 - 16 * j) - ln], bb = E[MFAC_SK(384 + 16 * j) + ln];
+    const float cc = O[MFAC_SK(127 - 16 * j) - ln], d = E[MFAC_SK(128 + 16 * j) + ln];
+    c[j].x = -a * kf[j][0] - bb * kf[j][2] - cc * kf[j][3] + d * kf[j][1];
+    c[j].y = -a * kf[j][1] - bb * kf[j][3] + cc * kf[j][2] - d * kf[j][0];
+  }
+#pragma unroll
+  for (int j = 8; j < 16; ++j) {
+    const float p = E[MFAC_SK(16 * j - 128) + ln], q = O[MFAC_SK(383 - 16 * j) - ln];
+    const float r = E[MFAC_SK(128 + 16 * j) + ln], t = O[MFAC_SK(639 - 16 * j) - ln];
+    c[j].x = p * kf[j][0] - q * kf[j][2] + r * kf[j][3] + t * kf[j][1];
+    c[j].y = p * kf[j][1] - q * kf[j][3] - r * kf[j][2] - t * kf[j][0];
+  }
+#undef MFAC_SK
+}
+// per-lane constants of the forward transform: (window x pre-twiddle) products of the 16 points this lane folds
+__device__ __forceinline__ void load_fold_constants(const FftTables& tab, float (&kf)[16][4], float2 (&tw)[16], int ln) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int m = 16 * j + ln;
+    const float2 pre = tab.pre[m];
+    const float w1 = j < 8 ? tab.window[FFT_H + 2 * m] : tab.window[2 * m - FFT_H];
+    const float w2 = j < 8 ? tab.window[FFT_H - 1 - 2 * m] : tab.window[3 * FFT_H - 1 - 2 * m];
+    kf[j][0] = w1 * pre.x; kf[j][1] = w1 * pre.y; kf[j][2] = w2 * pre.x; kf[j][3] = w2 * pre.y;
+    tw[j] = tab.w256[(ln * j) & 255];
+  }
+}
+
 __global__ void __launch_bounds__(F2_THREADS, 3)
 mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables tab, int64_t T, int64_t nf,
                    int64_t x_clip_stride, int64_t X_clip_stride) {
@@ -472,18 +505,9 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
       }
     }
   }
-  // per-lane constants
   float kf[16][4];
   float2 tw[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int m = 16 * j + ln;
-    const float2 pre = tab.pre[m];
-    const float w1 = j < 8 ? tab.window[FFT_H + 2 * m] : tab.window[2 * m - FFT_H];
-    const float w2 = j < 8 ? tab.window[FFT_H - 1 - 2 * m] : tab.window[3 * FFT_H - 1 - 2 * m];
-    kf[j][0] = w1 * pre.x; kf[j][1] = w1 * pre.y; kf[j][2] = w2 * pre.x; kf[j][3] = w2 * pre.y;
-    tw[j] = tab.w256[(ln * j) & 255];
-  }
+  load_fold_constants(tab, kf, tw, ln);
   sPost[tid] = tab.post[tid];
   sPost[tid + 128] = tab.post[tid + 128];
 
@@ -497,26 +521,8 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
   for (int it = 0; it < n_it; ++it) {
     const int f = it * (F2_THREADS / 16) + hw;
     const int fc = f < nframes ? f : nframes - 1;
-    const float* E = sE + fc * 144;
-    const float* O = sO + fc * 144;
     float2 c[16];
-    // fold + window + pre-twiddle (constants folded):  plane index r -> r + 16 (r >> 7), 16-lane groups never straddle
-#define MFAC_SK(r) ((r) + 16 * ((r) >> 7))
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a = O[MFAC_SK(383 - 16 * j) - ln], bb = E[MFAC_SK(384 + 16 * j) + ln];
-      const float cc = O[MFAC_SK(127 - 16 * j) - ln], d = E[MFAC_SK(128 + 16 * j) + ln];
-      c[j].x = -a * kf[j][0] - bb * kf[j][2] - cc * kf[j][3] + d * kf[j][1];
-      c[j].y = -a * kf[j][1] - bb * kf[j][3] + cc * kf[j][2] - d * kf[j][0];
-    }
-#pragma unroll
-    for (int j = 8; j < 16; ++j) {
-      const float p = E[MFAC_SK(16 * j - 128) + ln], q = O[MFAC_SK(383 - 16 * j) - ln];
-      const float r = E[MFAC_SK(128 + 16 * j) + ln], t = O[MFAC_SK(639 - 16 * j) - ln];
-      c[j].x = p * kf[j][0] - q * kf[j][2] + r * kf[j][3] + t * kf[j][1];
-      c[j].y = p * kf[j][1] - q * kf[j][3] - r * kf[j][2] - t * kf[j][0];
-    }
-#undef MFAC_SK
+    fold_frame(sE + fc * 144, sO + fc * 144, kf, c, ln);
     fft256_lanes16(c, tw, ex, PostSmem{sPost + ln}, ln);
     // X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2
     float2* dst = reinterpret_cast<float2*>(X + b * X_clip_stride + (f0 + fc) * FFT_N) + ln;
@@ -524,6 +530,81 @@ mdct512h256_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables
     for (int k2 = 0; k2 < 16; ++k2) {
       const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
       if (f < nframes) dst[16 * k2] = make_float2(c[fidx(k2)].x, -im);
+    }
+  }
+}
+
+// Short clips (nf <= 16, e.g. the 784-sample MNIST-shaped rows of the training step): one CTA packs several clips so
+// that its 32 frame slots stay busy.  Slot s -> clip s / nf, frame s % nf; every clip owns its own skewed segment.
+__global__ void __launch_bounds__(F2_THREADS, 2)
+mdct512h256_short_kernel(const float* __restrict__ x, float* __restrict__ X, FftTables tab, int64_t T, int nf, int cpc, int64_t B,
+                         int64_t x_clip_stride, int64_t X_clip_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int need = (nf - 1) * FFT_H + 2 * FFT_N;     // samples a clip's frames touch
+  const int pw = need / 2 / 128 * 144;               // skewed words per plane per clip
+  float* sE = reinterpret_cast<float*>(smem_raw);
+  float* sO = sE + cpc * pw;
+  float2* sEx = reinterpret_cast<float2*>(sO + cpc * pw);
+  float2* sPost = sEx + (F2_THREADS / 16) * F2_EX;
+  const int tid = threadIdx.x, ln = tid & 15, hw = tid >> 4;
+  const int64_t b0 = (int64_t)blockIdx.x * cpc;
+  const int nclips = (int)min((int64_t)cpc, B - b0);
+  const int nframes = nclips * nf;
+  const int per_clip4 = need / 4;
+  const int total4 = nclips * per_clip4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((x_clip_stride & 3) == 0);
+  constexpr int BATCH = 10;
+  for (int g0 = 0; g0 < total4; g0 += BATCH * F2_THREADS) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int g = g0 + tid + u * F2_THREADS;
+      const int cl = g / per_clip4, i4 = (g - cl * per_clip4) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < total4) {
+        const float* src = x + (b0 + cl) * x_clip_stride + i4;
+        if (aligned && i4 + 3 < T) v[u] = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (i4 < T) v[u].x = __ldg(src);
+          if (i4 + 1 < T) v[u].y = __ldg(src + 1);
+          if (i4 + 2 < T) v[u].z = __ldg(src + 2);
+          if (i4 + 3 < T) v[u].w = __ldg(src + 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int g = g0 + tid + u * F2_THREADS;
+      if (g < total4) {
+        const int cl = g / per_clip4, q = (g - cl * per_clip4) * 2;
+        const int ph = cl * pw + q + 16 * (q >> 7);
+        *reinterpret_cast<float2*>(sE + ph) = make_float2(v[u].x, v[u].z);
+        *reinterpret_cast<float2*>(sO + ph) = make_float2(v[u].y, v[u].w);
+      }
+    }
+  }
+  float kf[16][4];
+  float2 tw[16];
+  load_fold_constants(tab, kf, tw, ln);
+  sPost[tid] = tab.post[tid];
+  sPost[tid + 128] = tab.post[tid + 128];
+  __syncthreads();
+
+  float2* ex = sEx + hw * F2_EX;
+  const int n_it = (nframes + F2_THREADS / 16 - 1) / (F2_THREADS / 16);
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it) {
+    const int sl = it * (F2_THREADS / 16) + hw;
+    const int sc = sl < nframes ? sl : nframes - 1;
+    const int cl = sc / nf, fr = sc - cl * nf;
+    float2 c[16];
+    fold_frame(sE + cl * pw + fr * 144, sO + cl * pw + fr * 144, kf, c, ln);
+    fft256_lanes16(c, tw, ex, PostSmem{sPost + ln}, ln);
+    float2* dst = reinterpret_cast<float2*>(X + (b0 + cl) * X_clip_stride + (int64_t)fr * FFT_N) + ln;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
+      if (sl < nframes) dst[16 * k2] = make_float2(c[fidx(k2)].x, -im);
     }
   }
 }
@@ -815,9 +896,23 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
       MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
       configured2 = true;
     }
-    dim3 grid((unsigned)ceil_div<int64_t>(nf, F2_FRAMES), (unsigned)B);
     void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)B * ((double)T + (double)nf * N), stream);
-    mdct512h256_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(x, X, ts.fft, T, nf, io.in_clip_stride, io.out_clip_stride);
+    if (nf <= F2_FRAMES / 2) {
+      // short clips: pack clips into a CTA until its 32 frame slots are used
+      const int cpc = F2_FRAMES / (int)nf;
+      const int need = ((int)nf - 1) * FFT_H + 2 * FFT_N;
+      const size_t smem_s = (size_t)2 * cpc * (need / 2 / 128 * 144) * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
+      static bool configured3 = false;
+      if (!configured3) {
+        MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512h256_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured3 = true;
+      }
+      mdct512h256_short_kernel<<<(unsigned)ceil_div<int64_t>(B, cpc), F2_THREADS, smem_s, stream>>>(
+          x, X, ts.fft, T, (int)nf, cpc, B, io.in_clip_stride, io.out_clip_stride);
+    } else {
+      dim3 grid((unsigned)ceil_div<int64_t>(nf, F2_FRAMES), (unsigned)B);
+      mdct512h256_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(x, X, ts.fft, T, nf, io.in_clip_stride, io.out_clip_stride);
+    }
     profile_end(prof, stream);
     count_launch();
     return launch_status();
