@@ -71,6 +71,13 @@ def test_reference_test_case_verbatim(m):
     ((2, 511), 512, 256),         # T < N -> one zero-padded frame (mdct.py:491)
     ((2, 512), 512, 256),         # T == N
     ((1, 20), 16, 8),
+    # window 512 / hop 256 fast paths: packed short clips, partial CTAs, several CTAs / streams per clip, odd lengths
+    ((37, 784), 512, 256),        # nf = 2: 16 clips per CTA, ragged last CTA
+    ((5, 1300), 512, 256),        # nf = 4
+    ((3, 4607), 512, 256),        # nf = 16 (last packed size), odd T -> unaligned rows, scalar staging
+    ((3, 4864), 512, 256),        # nf = 18: first size of the one-clip-per-CTA kernel (partial CTA)
+    ((2, 9001), 512, 256),        # nf = 34: two CTAs per clip, odd row stride
+    ((2, 30011), 512, 256),       # nf = 116: several IMDCT streams per clip with a ragged tail
 ])
 def test_against_fp64_oracle(m, shape, N, hop):
     g = torch.Generator().manual_seed(sum(shape) + N + hop)
