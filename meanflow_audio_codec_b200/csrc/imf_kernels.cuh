@@ -188,6 +188,8 @@ struct LnModArgs {
   __nv_bfloat16* hind;       // tangent
   float* mu;                 // [B] or null
   float* rstd;               // [B] or null
+  int64_t m_stride;          // row stride of m in elements: Mp, or 0 when every row shares one modulation row
+                             // (samplers: the modulation depends on (t, h) only, which is constant over the batch)
 };
 
 template <bool TANGENT>
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(ROW_THREADS) lnmod_kernel(LnModArgs a, Dims d)
     mean_ncd = block_sum(acc, red) * inv_i;
   }
   if (threadIdx.x == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
-  const __nv_bfloat16* mrow = a.m + b * d.Mp;
+  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
   const __nv_bfloat16* mdrow = TANGENT ? a.md + b * d.Mp : nullptr;
   for (int p = threadIdx.x; p < d.Ip; p += blockDim.x) {
     const bool real = p < d.L || (p >= d.Lp && p - d.Lp < d.D);
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
     mean_ncd = warp_sum(acc) * inv_i;
   }
   if (lane == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
-  const __nv_bfloat16* mrow = a.m + b * d.Mp;
+  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = 8 * (lane + 32 * i);
