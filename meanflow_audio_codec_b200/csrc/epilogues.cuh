@@ -15,14 +15,33 @@ constexpr float LN_EPS = 1e-6f;  // flax.linen.LayerNorm(epsilon=1e-6)
 // GELU uses tanh.approx.f32 (one MUFU op): its 2^-11 relative error is far inside the bf16 rounding of
 // the values it feeds.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_fast(float a) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * a * (1.0f + tanh_fast(k0 * (a + k1 * a * a * a)));
+// gelu(a) = a (1/2 + 1/2 tanh(a (k0 + k0 k1 a^2)));  three packed multiplies, two packed FMAs and two MUFU per pair
+__device__ __forceinline__ float2 gelu_fast2(float2 a) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float2 t = f2mul(a, a);
+  const float2 arg = f2mul(a, f2fma(t, f2splat(k0k1), f2splat(k0)));
+  const float2 th = make_float2(tanh_fast(arg.x), tanh_fast(arg.y));
+  return f2mul(a, f2fma(th, f2splat(0.5f), f2splat(0.5f)));
 }
-__device__ __forceinline__ float dgelu_fast(float a) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float th = tanh_fast(k0 * (a + k1 * a * a * a));
-  return 0.5f * (1.0f + th) + 0.5f * a * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * a * a);
+// gelu'(a) = 1/2 (1 + th) + 1/2 a (1 - th^2) (k0 + 3 k0 k1 a^2)
+__device__ __forceinline__ float2 dgelu_fast2(float2 a) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float2 t = f2mul(a, a);
+  const float2 arg = f2mul(a, f2fma(t, f2splat(k0k1), f2splat(k0)));
+  const float2 th = make_float2(tanh_fast(arg.x), tanh_fast(arg.y));
+  const float2 q = f2mul(a, f2fma(t, f2splat(1.5f * k0k1), f2splat(0.5f * k0)));      // 1/2 a (k0 + 3 k0 k1 a^2)
+  const float2 s = f2fma(make_float2(-th.x, -th.y), th, f2splat(1.0f));                // 1 - th^2
+  return f2fma(q, s, f2fma(th, f2splat(0.5f), f2splat(0.5f)));
+}
+__device__ __forceinline__ float4 gelu_fast4(float4 a) {
+  const float2 lo = gelu_fast2(make_float2(a.x, a.y)), hi = gelu_fast2(make_float2(a.z, a.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// acc * gelu'(a)
+__device__ __forceinline__ float4 mul_dgelu_fast4(float4 acc, float4 a) {
+  const float2 lo = f2mul(make_float2(acc.x, acc.y), dgelu_fast2(make_float2(a.x, a.y)));
+  const float2 hi = f2mul(make_float2(acc.z, acc.w), dgelu_fast2(make_float2(a.z, a.w)));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ldg_bf4(const __nv_bfloat16* p) {
@@ -39,7 +58,10 @@ __device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
 }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  const float2 lo = f2add(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = f2add(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 constexpr int EPI_THREADS = 256;  // epilogue threads of the GEMM kernel (prefetch work split)
 struct BiasCol { float4 b; };
@@ -62,7 +84,7 @@ struct EpiBiasGelu {
     acc = add4(acc, c.b);
     const int64_t at = (int64_t)row * ld + col;
     if (a_out) st_bf4(a_out + at, acc);
-    st_bf4(g + at, make_float4(gelu_fast(acc.x), gelu_fast(acc.y), gelu_fast(acc.z), gelu_fast(acc.w)));
+    st_bf4(g + at, gelu_fast4(acc));
   }
 };
 // out = acc * gelu'(a)   (tangent through GELU, and the backward of GELU)
@@ -82,8 +104,7 @@ struct EpiMulDgelu {
   __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs& r, const ColRegs&) const {
     const int64_t at = (int64_t)row * ld + col;
     const float4 av = bf4_to_f4(r.av);
-    st_bf4(out + at, make_float4(acc.x * dgelu_fast(av.x), acc.y * dgelu_fast(av.y), acc.z * dgelu_fast(av.z),
-                                 acc.w * dgelu_fast(av.w)));
+    st_bf4(out + at, mul_dgelu_fast4(acc, av));
   }
 };
 // out = acc (+ bias)

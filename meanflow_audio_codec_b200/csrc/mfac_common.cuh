@@ -71,6 +71,26 @@ __device__ __forceinline__ void gelu_both(float a, float& g, float& dg) {
   dg = 0.5f * (1.0f + th) + 0.5f * a * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * a * a);
 }
 
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 -- one issue slot for two lanes of math).  The GEMM epilogues
+// are issue-bound, not FP32-pipe-bound, so halving the instruction count of their elementwise tails is a direct win.
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ua), "l"(ub));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ua), "l"(ub));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b),
+                     uc = *reinterpret_cast<unsigned long long*>(&c), r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(ua), "l"(ub), "l"(uc));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 f2splat(float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
