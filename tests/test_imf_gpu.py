@@ -194,3 +194,109 @@ def test_graphed_train_step_matches_eager(cuda):
     assert rel < 1e-5, rel
     # the update actually moved the weights
     assert float((flat_g - model.init(11)["params"].flat).norm()) > 0
+
+
+def test_loss_trajectory_with_fixed_draws(cuda):
+    """the reference re-draws the SAME (e, t, r) every step, so a training run is a deterministic
+    trajectory.  20 AdamW steps on the device against the fp64 oracle: per-step loss, per-example ||delta||^2 and the
+    final parameters (lr raised to 1e-3 so that the trajectory actually moves; Adam's sign-like updates amplify
+    bf16 rounding at larger rates)."""
+    import meanflow_audio_codec_b200 as m
+    D, L, C, nb, B, steps, lr = 128, 64, 32, 3, 48, 20, 1e-3
+    p_np = oracle_params(D, L, C, nb)
+    x, e, t, r = _inputs(D, B, seed=11)
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=to_device_tree(p_np), tx=m.adamw(lr, 1e-4))
+    strat = m.ImprovedMeanFlowLoss()
+    xd, ed = torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda()
+    td, rd = torch.from_numpy(t[:, 0].copy()).cuda(), torch.from_numpy(r[:, 0].copy()).cuda()
+    p_ref = as64(p_np)
+    mu = {k: np.zeros_like(v) for k, v in p_ref.items()}
+    nu = {k: np.zeros_like(v) for k, v in p_ref.items()}
+    x64, e64, t64, r64 = (a.astype(np.float64) for a in (x, e, t, r))
+    for step in range(steps):
+        loss, grads, aux = strat.compute_loss(state, 0, xd, noise=ed, t=td, r=rd, return_aux=True)
+        state = state.apply_gradients(grads=grads)
+        loss_ref, g_ref, aux_ref = imf_np.imf_loss_and_grads(p_ref, x64, e64, t64, r64)
+        p_ref, mu, nu = imf_np.adamw_step(p_ref, g_ref, mu, nu, step, lr=lr)
+        assert abs(float(loss) - loss_ref) < 1e-4, (step, float(loss), loss_ref)
+        assert rel_l2(aux["per_example"].cpu().numpy(), aux_ref["per_example"]) < TOL, step
+    got = tree_to_np(state.params)
+    num = sum(float(np.sum((got[k] - p_ref[k]) ** 2)) for k in p_ref)
+    den = sum(float(np.sum((p_ref[k] - p_np[k].astype(np.float64)) ** 2)) for k in p_ref)
+    assert den > 0 and (num / den) ** 0.5 < 0.1, (num, den)       # error relative to the distance travelled
+
+
+def test_reference_property_jvp_equals_reverse_mode(cuda):
+    """test/test_improved_mean_flow.py:57-100 restated against the C ABI: the forward-mode tangent du/dt the fused step
+    produces equals the directional derivative assembled from reverse-mode pieces of the oracle,
+    sum(du/dt) == sum_z grad_z(sum u) . v + sum grad_t(sum u) + sum grad_h(sum u)  (tangent (v, 1, 1) in (z, t, h))."""
+    import meanflow_audio_codec_b200 as m
+    from oracle import imf_torch
+    D, L, C, nb, B = 6, 64, 32, 2, 3          # the reference test's model and batch
+    p_np = oracle_params(D, L, C, nb)
+    x, e, t, r = _inputs(D, B, seed=2)
+    r = (0.5 * t).astype(np.float32)          # r = 0.5 t as in the reference test (:78)
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=to_device_tree(p_np), tx=m.adamw(1e-4, 1e-4))
+    loss, grads, aux = m.ImprovedMeanFlowLoss().compute_loss(
+        state, 0, torch.from_numpy(x).cuda(), noise=torch.from_numpy(e).cuda(), t=torch.from_numpy(t[:, 0].copy()).cuda(),
+        r=torch.from_numpy(r[:, 0].copy()).cuda(), return_aux=True)
+    p64 = {k: torch.from_numpy(v.astype(np.float64)) for k, v in p_np.items()}
+    x64, e64 = torch.from_numpy(x.astype(np.float64)), torch.from_numpy(e.astype(np.float64))
+    t64, r64 = torch.from_numpy(t.astype(np.float64)), torch.from_numpy(r.astype(np.float64))
+    lat = imf_torch.encode(p64, x64)
+    z = ((1 - t64) * x64 + (0.001 + 0.999 * t64) * e64).requires_grad_(True)
+    tt = t64.clone().requires_grad_(True)
+    hh = (t64 - r64).clone().requires_grad_(True)
+    v = imf_torch.forward(p64, z.detach(), torch.cat([t64, torch.zeros_like(t64)], 1), lat).detach()
+    u = imf_torch.forward(p64, z, torch.cat([tt, hh], 1), lat)
+    gz, gt, gh = torch.autograd.grad(u.sum(), (z, tt, hh))
+    directional = float((gz * v).sum() + gt.sum() + gh.sum())
+    got = float(aux["dudt"].double().sum())
+    scale = float(aux["dudt"].double().abs().sum())     # the sum cancels heavily: bf16 tolerance is relative to sum |du/dt|
+    assert abs(got - directional) <= TOL * scale, (got, directional, scale)
+
+
+@pytest.mark.parametrize("B", [4096, 18944])
+def test_full_size_step_properties(cuda, B):
+    """BASELINE sizes (D=1024, L=256, C=128, 8 blocks) where the oracle is too slow: size-independent properties.
+    (1) rows are independent: the first 128 rows of the big batch give the same per-example ||delta||^2, u and du/dt as a
+        128-row batch run on its own (same explicit draws);  (2) the gradient is linear in the rows: grads(B) * B equals
+        the sum of the two half-batch gradients * B/2;  (3) r = t rows have v_pred == u exactly (their (t - r) is 0)."""
+    import meanflow_audio_codec_b200 as m
+    D, L, C, nb = 1024, 256, 128, 8
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    params = model.init(42)["params"]
+    state = m.TrainState.create(apply_fn=model.apply, params=params, tx=m.adamw(1e-4, 1e-4))
+    strat = m.ImprovedMeanFlowLoss()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = 2 * torch.rand(B, D, device="cuda", generator=g) - 1
+    e = torch.randn(B, D, device="cuda", generator=g)
+    n = torch.randn(2, B, device="cuda", generator=g)
+    t, r = torch.sigmoid(n[0] - 0.4), torch.sigmoid(n[1] - 0.4)
+    t, r = torch.maximum(t, r), torch.minimum(t, r)
+    r = torch.where(torch.arange(B, device="cuda") < B // 2, t, r)
+    loss, grads, aux = strat.compute_loss(state, 0, x, noise=e, t=t, r=r, return_aux=True)
+    big = {k: v.clone() for k, v in aux.items()}
+    gflat = grads.flat.clone()
+    assert torch.isfinite(loss) and torch.isfinite(gflat).all()
+    # (1) row independence
+    _, _, small = strat.compute_loss(state, 0, x[:128].contiguous(), noise=e[:128].contiguous(), t=t[:128].contiguous(),
+                                     r=r[:128].contiguous(), return_aux=True)
+    for k in ("u", "dudt", "per_example"):
+        a, b = big[k][:128].double(), small[k].double()
+        assert float((a - b).norm() / b.norm()) < 1e-5, k
+    # (2) linearity over rows (split-K atomics reorder the sums; fp32)
+    h = B // 2
+    _, g1 = strat.compute_loss(state, 0, x[:h].contiguous(), noise=e[:h].contiguous(), t=t[:h].contiguous(), r=r[:h].contiguous())
+    g1 = g1.flat.clone()
+    _, g2 = strat.compute_loss(state, 0, x[h:].contiguous(), noise=e[h:].contiguous(), t=t[h:].contiguous(), r=r[h:].contiguous())
+    comb = 0.5 * (g1 + g2.flat)
+    assert float((comb - gflat).norm() / gflat.norm()) < 2e-3
+    # (3) boundary rows
+    tr0 = (t - r) == 0
+    assert int(tr0.sum()) >= B // 2
+    delta_u = big["u"] - (0.999 * e - x)
+    s_u = (delta_u[tr0] ** 2).sum(1)
+    assert float((s_u - big["per_example"][tr0]).abs().max() / s_u.max()) < 1e-5
