@@ -96,7 +96,8 @@ struct EpiMulDgelu {
   int64_t ld;
   struct Regs { uint2 av; };
   using ColRegs = NoRegs;
-  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int N, int etid) const {
+    bn = min(bn, N - n0);   // never reach past the last column (partial last tile)
     l2_prefetch_tile<2>(a, ld, m0, n0, bn, M, etid, EPI_THREADS);
   }
   __device__ __forceinline__ void load_col(int, ColRegs&) const {}
@@ -151,7 +152,8 @@ struct EpiAffineResidual {
   float alpha;
   struct Regs { float4 r; };
   using ColRegs = BiasCol;
-  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int N, int etid) const {
+    bn = min(bn, N - n0);   // never reach past the last column (partial last tile)
     if (res && (ld & 31) == 0) l2_prefetch_tile<4>(res, ld, m0, n0, bn, M, etid, EPI_THREADS);
   }
   __device__ __forceinline__ void load_col(int col, ColRegs& c) const { c.b = bias ? ldg_f4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -180,7 +182,8 @@ struct EpiBlockOut {
   float inv_nb;
   struct Regs { uint2 s2; float4 xo; };
   using ColRegs = BiasCol;
-  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int N, int etid) const {
+    bn = min(bn, N - n0);   // never reach past the last column (partial last tile)
     l2_prefetch_tile<2>(m, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
     l2_prefetch_tile<4>(x_old, ldx, m0, n0, bn, M, etid, EPI_THREADS);
   }
@@ -212,7 +215,8 @@ struct EpiBlockOutTangent {
   float inv_nb;
   struct Regs { uint2 s2, s2d, ov; float4 xd; };
   using ColRegs = NoRegs;
-  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int, int etid) const {
+  __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int N, int etid) const {
+    bn = min(bn, N - n0);   // never reach past the last column (partial last tile)
     l2_prefetch_tile<2>(m, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
     l2_prefetch_tile<2>(md, ldm, m0, s2_off + n0, bn, M, etid, EPI_THREADS);
     l2_prefetch_tile<2>(o, ldx, m0, n0, bn, M, etid, EPI_THREADS);
