@@ -1,0 +1,107 @@
+// XLA FFI (jax.ffi) handlers over the libmfac C ABI -- the "thin C-ABI layer (jax.ffi custom calls)" of the north star.
+//
+// NOT compiled in the build image (no jaxlib, hence no xla/ffi/api/ffi.h); built by meanflow_audio_codec_b200/jax_ffi/
+// build.py on a box where `python -c "import jax.ffi; print(jax.ffi.include_dir())"` works:
+//   g++ -O2 -std=c++17 -shared -fPIC -I$(jax include dir) -I<repo>/include -I/usr/local/cuda/include \
+//       mfac_jax_ffi.cc -L<repo>/meanflow_audio_codec_b200 -lmfac -Wl,-rpath,'$ORIGIN/..' -o libmfac_jax_ffi.so
+// Every handler only unpacks buffers and forwards to the C ABI on XLA's stream; shapes are validated on the Python side
+// (jax_ffi/__init__.py) exactly as the reference validates them (preprocessing/mdct.py:189-194,247-250).
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+
+#include "mfac.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static ffi::Error status_of(int rc) {
+  return rc == 0 ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInternal, mfac_status_string(rc));
+}
+
+// x[B, T] -> X[B, nf, N]            (ref: preprocessing/mdct.py:143-198, direct branch :317-327)
+static ffi::Error MdctImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> x, ffi::ResultBuffer<ffi::F32> X, int32_t window_size,
+                           int32_t hop_size) {
+  const auto d = x.dimensions();
+  if (d.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "mfac_mdct expects x[B, T]");
+  return status_of(mfac_mdct_f32(x.typed_data(), X->typed_data(), d[0], d[1], window_size, hop_size, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MfacMdct, MdctImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("window_size")
+                                  .Attr<int32_t>("hop_size"));
+
+// X[B, nf, N] -> y[B, (nf-1) hop + 2N]   (ref: preprocessing/mdct.py:201-256, :330-340, :517-540)
+static ffi::Error ImdctImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> X, ffi::ResultBuffer<ffi::F32> y, int32_t window_size,
+                            int32_t hop_size) {
+  const auto d = X.dimensions();
+  if (d.size() != 3 || d[2] != window_size) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "mfac_imdct expects X[B, nf, N]");
+  return status_of(mfac_imdct_f32(X.typed_data(), y->typed_data(), d[0], d[1], window_size, hop_size, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MfacImdct, ImdctImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("window_size")
+                                  .Attr<int32_t>("hop_size"));
+
+// model.apply({"params": p}, x, time, latents)   (ref: models/mlp_flow.py:199-230)
+// operands: flat params (jax.flatten_util.ravel_pytree order == the layout of include/mfac.h), bf16 shadow (bytes),
+// x[B, D], time[B, 2], latents[B, L];  results: out[B, D], workspace scratch (bytes, sized by mfac_workspace_bytes)
+static ffi::Error MlpForwardImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::U8> shadow,
+                                 ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> time, ffi::Buffer<ffi::F32> latents,
+                                 ffi::ResultBuffer<ffi::F32> out, ffi::ResultBuffer<ffi::U8> ws, int32_t D, int32_t L, int32_t C,
+                                 int32_t nb) {
+  MfacMlpDims dims{D, L, C, nb};
+  const int64_t B = x.dimensions()[0];
+  return status_of(mfac_mlp_forward(&dims, params.typed_data(), shadow.typed_data(), x.typed_data(), time.typed_data(),
+                                    latents.typed_data(), out->typed_data(), B, ws->typed_data(), ws->size_bytes(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MfacMlpForward, MlpForwardImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int32_t>("D")
+                                  .Attr<int32_t>("L")
+                                  .Attr<int32_t>("C")
+                                  .Attr<int32_t>("nb"));
+
+// ImprovedMeanFlowLoss.compute_loss -> (loss, grads)   (ref: trainers/loss_strategies.py:227-280)
+// operands: flat params, shadow, x[B, D], e[B, D], t[B], r[B];  results: loss[], grads[P], workspace scratch
+static ffi::Error ImfLossGradImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::U8> shadow,
+                                  ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> e, ffi::Buffer<ffi::F32> t,
+                                  ffi::Buffer<ffi::F32> r, ffi::ResultBuffer<ffi::F32> loss, ffi::ResultBuffer<ffi::F32> grads,
+                                  ffi::ResultBuffer<ffi::U8> ws, int32_t D, int32_t L, int32_t C, int32_t nb) {
+  MfacMlpDims dims{D, L, C, nb};
+  MfacImfConfig cfg{0.001f, 0.999f, -0.4f, 1.0f, 0.5f, 1e-3f, 1, 0, 0, 0, nullptr};
+  const int64_t B = x.dimensions()[0];
+  return status_of(mfac_imf_loss_grad(&dims, &cfg, params.typed_data(), shadow.typed_data(), x.typed_data(), e.typed_data(),
+                                      t.typed_data(), r.typed_data(), loss->typed_data(), grads->typed_data(), nullptr, B,
+                                      ws->typed_data(), ws->size_bytes(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MfacImfLossGrad, ImfLossGradImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int32_t>("D")
+                                  .Attr<int32_t>("L")
+                                  .Attr<int32_t>("C")
+                                  .Attr<int32_t>("nb"));
