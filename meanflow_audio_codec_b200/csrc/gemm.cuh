@@ -437,8 +437,13 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
   // covers the machine.
   int bn = force_bn;
   if (bn == 0) {
-    const int tiles256 = ceil_div(M, GEMM_BM) * ceil_div(N, 256);
-    bn = (N % 256 == 0 && tiles256 >= num_sms()) ? 256 : 128;
+    // rounds of the persistent grid x relative cost of one tile (a 128x256 tile does twice the work of a 128x128 one
+    // at ~13 % better tensor efficiency): e.g. 160 tiles of 256 on 148 SMs are two rounds, 320 tiles of 128 only three
+    // half-size ones.
+    const int sms = num_sms();
+    const int t256 = ceil_div(M, GEMM_BM) * ceil_div(N, 256), t128 = ceil_div(M, GEMM_BM) * ceil_div(N, 128);
+    const double c256 = (double)ceil_div(t256, sms) * 1.74, c128 = (double)ceil_div(t128, sms);
+    bn = (N % 256 == 0 && c256 <= c128) ? 256 : 128;
   }
   int splits = 1;
   if (split_k) {
