@@ -138,8 +138,9 @@ int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_
   return MFAC_SUCCESS;
 }
 
-int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* /*partial*/, float* out, int kind, int limit, const Dims& d,
-           cudaStream_t s, int ncols = 0) {
+// out[map(col)] += sum_rows G[:, col]  (bias gradients; out is zeroed with the rest of the gradient before the backward)
+int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* out, int kind, int limit, const Dims& d, cudaStream_t s,
+           int ncols = 0) {
   if (ncols == 0) ncols = ld;
   const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
   colsum_atomic_vec_kernel<<<dim3(ceil_div(ncols, 256), R), 256, 0, s>>>(G, ld, ncols, B, out, kind, limit, d);
@@ -170,7 +171,7 @@ struct LossGradPlan {
   __nv_bfloat16 *gcd, *md, *hind, *gd;
   float* xd;
   // loss / backward
-  float *row_loss, *g_x, *g_lat, *partial;
+  float *row_loss, *g_x, *g_lat;
   __nv_bfloat16 *g_o, *g_a, *g_m, *g_ac, *g_latb, *g_ae;
 
   void plan(Arena& ar, const Dims& d, int64_t B) {
@@ -208,7 +209,6 @@ struct LossGradPlan {
     row_loss = ar.take<float>(B);
     g_x = ar.take<float>(B * d.Dp);
     g_lat = ar.take<float>(B * d.Lp);
-    partial = ar.take<float>(ceil_div<int64_t>(B, COLSUM_VROWS) * d.Mp);
     g_o = ar.take<__nv_bfloat16>(B * d.Dp);
     g_a = ar.take<__nv_bfloat16>(B * d.Ip);
     g_m = ar.take<__nv_bfloat16>(B * d.Mp);
@@ -391,26 +391,26 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
     MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
     MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
-    MFAC_OK(colsum(p.g_a, d.Ip, B, p.partial, gk + d.o_m1b, MAP_CM, 0, d, s));
+    MFAC_OK(colsum(p.g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, s));
     // g_hin = g_a W1^T goes out in bf16 straight into g_m[:, Ip:2Ip]: it IS the shift gradient (hin = (1+s1) n + shift)
     MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
     MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
-    MFAC_OK(colsum(p.g_m, d.Mp, B, p.partial, gk + d.o_c2b, MAP_MM, 0, d, s, 2 * d.Ip));  // s1 | shift thirds
+    MFAC_OK(colsum(p.g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, s, 2 * d.Ip));  // s1 | shift thirds
     MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
     MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, 1, d}, s));
-    MFAC_OK(colsum(p.g_ac, d.Cp, B, p.partial, gk + d.o_c1b, MAP_ID, d.C, d, s));
+    MFAC_OK(colsum(p.g_ac, d.Cp, B, gk + d.o_c1b, MAP_ID, d.C, d, s));
   }
   // ---- encoder backward
   f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);
   count_launch();
   MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, 1, d}, s));
-  MFAC_OK(colsum(p.g_latb, d.Lp, B, p.partial, grads + d.o_e2b, MAP_ID, d.L, d, s));
+  MFAC_OK(colsum(p.g_latb, d.Lp, B, grads + d.o_e2b, MAP_ID, d.L, d, s));
   MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, s));
   MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, 1, d}, s));
-  MFAC_OK(colsum(p.g_ae, d.Hep, B, p.partial, grads + d.o_e1b, MAP_ID, d.He, d, s));
+  MFAC_OK(colsum(p.g_ae, d.Hep, B, grads + d.o_e1b, MAP_ID, d.He, d, s));
   // ---- optional intermediates for parity tests
   if (aux) {
     const unsigned nbk = blocks_for(B * d.D, 256);
