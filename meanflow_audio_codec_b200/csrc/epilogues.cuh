@@ -71,6 +71,7 @@ struct NoRegs {};
 struct EpiBiasGelu {
   static constexpr const char* name = "bias_gelu";
   static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = false;
   const float* bias;        // padded fp32 [N]
   __nv_bfloat16* g;         // [M, ld]
   __nv_bfloat16* a_out;     // [M, ld] or null
@@ -91,6 +92,7 @@ struct EpiBiasGelu {
 struct EpiMulDgelu {
   static constexpr const char* name = "mul_dgelu";
   static constexpr int kPrefetchDepth = 2;
+  static constexpr bool kTmaStore = false;
   const __nv_bfloat16* a;   // [M, ld]
   __nv_bfloat16* out;       // [M, ld]
   int64_t ld;
@@ -112,6 +114,7 @@ struct EpiMulDgelu {
 struct EpiLinearBf16 {
   static constexpr const char* name = "linear_bf16";
   static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = false;
   const float* bias;  // or null
   __nv_bfloat16* out;
   int64_t ld;
@@ -127,6 +130,7 @@ struct EpiLinearBf16 {
 struct EpiLinearF32 {
   static constexpr const char* name = "linear_f32";
   static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = false;
   const float* bias;  // or null
   float* out;
   int64_t ld;
@@ -144,6 +148,7 @@ struct EpiLinearF32 {
 struct EpiAffineResidual {
   static constexpr const char* name = "affine_residual";
   static constexpr int kPrefetchDepth = 2;
+  static constexpr bool kTmaStore = false;
   const float* bias;       // [N] or null
   const float* res;        // [M, ld] or null
   float* out_f;            // [M, ld] or null (may alias res)
@@ -172,6 +177,7 @@ struct EpiAffineResidual {
 struct EpiBlockOut {
   static constexpr const char* name = "block_out";
   static constexpr int kPrefetchDepth = 2;
+  static constexpr bool kTmaStore = false;
   const float* bias;          // padded [Dp]
   const __nv_bfloat16* m;     // [M, Mp]; s2 at column offset s2_off
   const float* x_old;         // [M, Dp]
@@ -205,6 +211,7 @@ struct EpiBlockOut {
 struct EpiBlockOutTangent {
   static constexpr const char* name = "block_out_tangent";
   static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = false;
   const __nv_bfloat16* m;     // primal modulation  [M, Mp]
   const __nv_bfloat16* md;    // tangent modulation [M, Mp]
   const __nv_bfloat16* o;     // primal o [M, Dp]
@@ -234,6 +241,77 @@ struct EpiBlockOutTangent {
                                    (acc.y * (1.0f + s2.y) + ov.y * s2d.y) * inv_nb + xd.y,
                                    (acc.z * (1.0f + s2.z) + ov.z * s2d.z) * inv_nb + xd.z,
                                    (acc.w * (1.0f + s2.w) + ov.w * s2d.w) * inv_nb + xd.w));
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// TMA-store functors (gemm.cuh: epilogue_tile_tma).  compute() sees 32 consecutive columns of ONE row (the accumulator's
+// native layout) and returns them as 16 packed bf16 pairs; N must be a multiple of 64.
+// ---------------------------------------------------------------------------------------
+struct EpiTmaps;
+int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer, int swizzle_bytes);
+
+// out = acc (+ bias) -> bf16
+struct EpiLinearBf16Tma {
+  static constexpr const char* name = "linear_bf16";
+  static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = true;
+  static constexpr int kNumOut = 1;
+  const float* bias;  // or null
+  __nv_bfloat16* out;
+  int64_t ld;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  template <class Maps>
+  int make_maps(Maps& m, int M, int N) const {
+    const int rc = make_tmap_bf16_sw(&m.m[0], out, N, M, ld, 64, 32, 128);
+    m.m[1] = m.m[0];
+    return rc;
+  }
+  __device__ __forceinline__ void compute(int col0, const float (&acc)[32], uint32_t (&o)[16]) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = bias ? ldg_f4(bias + col0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = add4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), b);
+      o[2 * q] = pack_bf16(v.x, v.y);
+      o[2 * q + 1] = pack_bf16(v.z, v.w);
+    }
+  }
+  __device__ __forceinline__ void store_row(int row, int col0, const float (&acc)[32]) const {
+    for (int j = 0; j < 32; ++j) out[(int64_t)row * ld + col0 + j] = __float2bfloat16(acc[j] + (bias ? bias[col0 + j] : 0.f));
+  }
+};
+
+// g = gelu(acc + bias) -> bf16  (forward passes that keep no pre-activation: v pass, samplers, mixer / convnet)
+struct EpiBiasGeluTma {
+  static constexpr const char* name = "bias_gelu";
+  static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = true;
+  static constexpr int kNumOut = 1;
+  const float* bias;
+  __nv_bfloat16* g;
+  int64_t ld;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  template <class Maps>
+  int make_maps(Maps& m, int M, int N) const {
+    const int rc = make_tmap_bf16_sw(&m.m[0], g, N, M, ld, 64, 32, 128);
+    m.m[1] = m.m[0];
+    return rc;
+  }
+  __device__ __forceinline__ void compute(int col0, const float (&acc)[32], uint32_t (&o)[16]) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = add4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), ldg_f4(bias + col0 + 4 * q));
+      const float4 gv = gelu_fast4(v);
+      o[2 * q] = pack_bf16(gv.x, gv.y);
+      o[2 * q + 1] = pack_bf16(gv.z, gv.w);
+    }
+  }
+  __device__ __forceinline__ void store_row(int row, int col0, const float (&acc)[32]) const {
+    for (int j = 0; j < 32; ++j) {
+      const float v = acc[j] + bias[col0 + j];
+      g[(int64_t)row * ld + col0 + j] = __float2bfloat16(gelu_fast2(make_float2(v, v)).x);
+    }
   }
 };
 

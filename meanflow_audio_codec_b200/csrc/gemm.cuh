@@ -44,16 +44,19 @@ constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_REGS_LAUNCH = 168;  // 65536 / 384 rounded down to a multiple of 8
 constexpr int GEMM_REGS_CTRL = 56;
 constexpr int GEMM_REGS_EPI = 224;     // 128 * 40 + 256 * 232 == 384 * 168
-constexpr int GEMM_SMEM_BUDGET = 196608;  // bytes of operand stages
 
-template <int BN>
+constexpr int GEMM_SMEM_TOTAL = 232448 - 1024 /*align slack*/ - 256 /*barriers*/;  // 227 KB per CTA
+
+template <int BN, bool TMA_EPI = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES;
+  // per-warp epilogue staging: one 32x32 fp32 transpose buffer, or two 32x64 bf16 tiles for the TMA-store epilogue
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * (TMA_EPI ? 8192 : 4096);
+  static constexpr int STAGES_MAX = (GEMM_SMEM_TOTAL - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_MAX > 6 ? 6 : STAGES_MAX;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // per-warp 32x32 fp32 transpose buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
@@ -73,6 +76,56 @@ struct GemmShape {
   int splits;        // split-K factor (1 = none); work item = tile * splits + split
   int kb_per_split;  // 64-wide k-blocks per split
 };
+
+// Output tensor maps of the TMA-store epilogues (bf16 outputs, 32 x 32 boxes, 64-byte swizzle)
+struct EpiTmaps {
+  CUtensorMap m[2];
+};
+int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer, int swizzle_bytes);
+
+// TMA-store epilogue for functors with ONE plain bf16 output and a per-column vector operand (Epi::kTmaStore): the
+// accumulator stays in its native layout (lane == row), the functor turns 2 x 32 columns into packed bf16, eight
+// 16-byte shared-memory stores lay a 32 x 64 tile down in the 128-byte-swizzled layout the tensor map expects, and ONE
+// elected lane hands it to the TMA engine (full 128-byte lines; two staging tiles per warp alternate).  Compared with
+// the transposed path: 16 instead of 128 shared-memory wavefronts per 64 columns and no global store instructions at
+// all -- the LSU/L1 path was the bottleneck of the store-bound K = 128 GEMMs.  Out-of-range rows are clipped by the
+// tensor map; N must be a multiple of 64.
+template <int BN, class Epi>
+__device__ __forceinline__ void epilogue_tile_tma(const Epi& epi, const GemmShape& shape, const EpiTmaps& maps, uint8_t* stage,
+                                                  uint32_t taddr, int row0, int n0, int half, int lane, uint64_t* tfull,
+                                                  uint32_t aph, uint32_t& parity) {
+  constexpr int NCH = BN / 128;                    // 64-column chunks handled by this warp: c = half + 2 j
+  mbar_wait(tfull, aph);
+  tc_fence_after();
+  const int sw = lane & 7;                         // 128-byte swizzle: 16-byte piece p of row r sits at p ^ (r & 7)
+#pragma unroll
+  for (int j = 0; j < (NCH > 0 ? NCH : 1); ++j) {
+    const int c = half + 2 * j;
+    const int col0 = n0 + c * 64;
+    if (c * 64 >= BN || col0 >= shape.N) break;    // warp-uniform
+    float acc[64];
+    tmem_ld_32x32(taddr + c * 64, *reinterpret_cast<float(*)[32]>(&acc[0]));
+    tmem_ld_32x32(taddr + c * 64 + 32, *reinterpret_cast<float(*)[32]>(&acc[32]));
+    tmem_ld_wait();
+    uint32_t o[32];
+    epi.compute(col0, *reinterpret_cast<const float(*)[32]>(&acc[0]), *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+    epi.compute(col0 + 32, *reinterpret_cast<const float(*)[32]>(&acc[32]), *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+    if (lane == 0) tma_store_wait_read<1>();       // the tile written two chunks ago has been read by the engine
+    __syncwarp();
+    uint8_t* buf = stage + (parity & 1) * 4096;
+    uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) rowp[p ^ sw] = make_uint4(o[4 * p], o[4 * p + 1], o[4 * p + 2], o[4 * p + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&maps.m[0], buf, col0, row0);
+      tma_store_commit();
+    }
+    ++parity;
+  }
+}
 
 // One epilogue warp's share of one output tile: 32 rows (its TMEM lane quarter) x every other 32-column chunk.
 // FULL = the tile lies entirely inside the matrix (no row / column predicates in the hot loop).
@@ -160,9 +213,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& s
 
 template <int BN, bool A_MN, bool B_MN, bool FULL, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape,
-                    Epi epi) {
-  using Cfg = GemmCfg<BN>;
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ EpiTmaps tmOut, GemmShape shape, Epi epi) {
+  using Cfg = GemmCfg<BN, Epi::kTmaStore>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -286,8 +339,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;        // which of the quarter's two warps: even / odd chunks
     const int etid = threadIdx.x - 128;      // 0 .. 32 * GEMM_EPI_WARPS - 1
-    float4* st = reinterpret_cast<float4*>(sStage + (warp - 4) * 4096);  // [32 rows][8 x 16 B], piece ^= row & 7
-    uint32_t it = 0;
+    float4* st = reinterpret_cast<float4*>(sStage + (warp - 4) * (Cfg::STAGING_BYTES / GEMM_EPI_WARPS));
+    uint32_t it = 0, tma_parity = 0;
     // The functor's global operands of the first tile are pulled into L2 while its MMAs run; every later
     // tile's are requested one tile ahead (the register prefetch inside a tile then only sees L2 latency).
     if ((int)blockIdx.x < num_items) {
@@ -305,10 +358,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (nt != tile) epi.prefetch((nt / n_tiles) * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
       }
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
+      if constexpr (Epi::kTmaStore)
+        epilogue_tile_tma<BN>(epi, shape, tmOut, reinterpret_cast<uint8_t*>(st), taddr, m0 + quarter * 32, n0, half, lane,
+                              &tfull_bar[as], aph, tma_parity);
+      else
+        epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if constexpr (Epi::kTmaStore) {
+      if (lane == 0) tma_store_wait_all();   // the staging buffers must outlive the engine's reads
+      __syncwarp();
     }
   }
 
@@ -345,13 +406,17 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmShape shape, 
       acc[j] = fmaf(a, b, acc[j]);
     }
   }
+  if constexpr (Epi::kTmaStore) {
+    epi.store_row(row, col0, acc);   // debug path of the TMA-store functors: plain stores
+  } else {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    typename Epi::Regs regs;
-    typename Epi::ColRegs cregs;
-    epi.load_col(col0 + j, cregs);
-    epi.load(row, col0 + j, regs);
-    epi.frag(row, col0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), regs, cregs);
+    for (int j = 0; j < 32; j += 4) {
+      typename Epi::Regs regs;
+      typename Epi::ColRegs cregs;
+      epi.load_col(col0 + j, cregs);
+      epi.load(row, col0 + j, regs);
+      epi.frag(row, col0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), regs, cregs);
+    }
   }
 }
 
@@ -375,7 +440,7 @@ void profile_end(void* token, cudaStream_t s);
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
                    cudaStream_t stream, int splits) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, Epi::kTmaStore>;
   CUtensorMap tmA, tmB;
   if (A_MN) {
     MFAC_OK(make_tmap_bf16(&tmA, A.ptr, M, K, A.ld, 64, 64));
@@ -407,8 +472,15 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   const int items = tiles * splits;
   const int grid = items < num_sms() ? items : num_sms();
   GemmShape shape{M, N, K, splits, kbps};
+  EpiTmaps maps;
+  if constexpr (Epi::kTmaStore) {
+    MFAC_OK(epi.make_maps(maps, M, N));
+  } else {
+    maps.m[0] = tmA;   // unused by the kernel; any valid descriptor
+    maps.m[1] = tmA;
+  }
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, maps, shape, epi);
   profile_end(prof, stream);
   count_launch();
   return launch_status();
@@ -469,6 +541,7 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
 struct EpiStoreF32 {
   static constexpr const char* name = "store_f32";
   static constexpr int kPrefetchDepth = 1;
+  static constexpr bool kTmaStore = false;
   struct Regs {};
   struct ColRegs {};
   float* C;

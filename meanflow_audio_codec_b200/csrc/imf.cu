@@ -46,6 +46,20 @@ int gemm_dw(const __nv_bfloat16* Act, int lda, const __nv_bfloat16* G, int ldg, 
                                  /*split_k=*/true);
 }
 
+// bias + GELU (+ keep pre-activation) and plain linear -> bf16.  Store-bound shapes (small K: the modulation MLP) go
+// through the TMA-store epilogue; compute-bound ones keep the transposed epilogue and its deeper operand ring (measured:
+// 35 vs 48 us for M=18944, N=3584, K=128, but 58 vs 53 us for N=K=1280).
+int gemm_bias_gelu(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const float* bias,
+                   __nv_bfloat16* g, __nv_bfloat16* a, int64_t ld, cudaStream_t s) {
+  if (a || N % 64 != 0 || K > 256) return gemm_fwd(A, lda, W, M, N, K, EpiBiasGelu{bias, g, a, ld}, s);
+  return gemm_fwd(A, lda, W, M, N, K, EpiBiasGeluTma{bias, g, ld}, s);
+}
+int gemm_linear_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const float* bias,
+                     __nv_bfloat16* out, int64_t ld, cudaStream_t s) {
+  if (N % 64 != 0 || K > 256) return gemm_fwd(A, lda, W, M, N, K, EpiLinearBf16{bias, out, ld}, s);
+  return gemm_fwd(A, lda, W, M, N, K, EpiLinearBf16Tma{bias, out, ld}, s);
+}
+
 // NV of the vectorised row kernels, or 0 when the geometry needs the generic (padded) kernels.
 inline int vec_rows(const Dims& d) {
   if (d.D != d.Dp || d.L != d.Lp || d.Ip % 256 != 0 || d.Ip > 2048) return 0;
@@ -119,11 +133,11 @@ int forward_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* cond, con
   for (int k = 0; k < d.nb; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
-    MFAC_OK(gemm_fwd(cond, d.Cp, w + d.s_c1w, Mc, d.Cp, d.Cp, EpiBiasGelu{bias + d.b_c1, sc.gc, nullptr, d.Cp}, s));
-    MFAC_OK(gemm_fwd(sc.gc, d.Cp, w + d.s_c2w, Mc, d.Mp, d.Cp, EpiLinearBf16{bias + d.b_c2, sc.m, d.Mp}, s));
+    MFAC_OK(gemm_bias_gelu(cond, d.Cp, w + d.s_c1w, Mc, d.Cp, d.Cp, bias + d.b_c1, sc.gc, nullptr, d.Cp, s));
+    MFAC_OK(gemm_linear_bf16(sc.gc, d.Cp, w + d.s_c2w, Mc, d.Mp, d.Cp, bias + d.b_c2, sc.m, d.Mp, s));
     LnModArgs la{lat, x, sc.m, sc.hin, nullptr, nullptr, nullptr, nullptr, nullptr, m_stride};
     MFAC_OK(lnmod(false, la, d, B, s));
-    MFAC_OK(gemm_fwd(sc.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiBiasGelu{bias + d.b_m1, sc.g, nullptr, d.Ip}, s));
+    MFAC_OK(gemm_bias_gelu(sc.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sc.g, nullptr, d.Ip, s));
     MFAC_OK(gemm_fwd(sc.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
                      EpiBlockOut{bias + d.b_m2, sc.m, x, x, nullptr, m_stride, d.Dp, 2 * d.Ip, inv_nb}, s));
   }
@@ -133,7 +147,7 @@ int forward_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* cond, con
 // latents = enc2(gelu(enc1(x)));  keeps a_e / g_e when asked (backward)
 int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_bfloat16* a_e, __nv_bfloat16* g_e, float* lat,
                  int64_t B, cudaStream_t s) {
-  MFAC_OK(gemm_fwd(xb, d.Dp, sh.w + d.s_e1w, (int)B, d.Hep, d.Dp, EpiBiasGelu{sh.b + d.b_e1, g_e, a_e, d.Hep}, s));
+  MFAC_OK(gemm_bias_gelu(xb, d.Dp, sh.w + d.s_e1w, (int)B, d.Hep, d.Dp, sh.b + d.b_e1, g_e, a_e, d.Hep, s));
   MFAC_OK(gemm_fwd(g_e, d.Hep, sh.w + d.s_e2w, (int)B, d.Lp, d.Hep, EpiLinearF32{sh.b + d.b_e2, lat, d.Lp}, s));
   return MFAC_SUCCESS;
 }
@@ -356,13 +370,13 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp;
     const float* xd_in = k == 0 ? p.v : p.xd;
     // modulation, primal and tangent
-    MFAC_OK(gemm_fwd(p.cond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiBiasGelu{bias + d.b_c1, sb.gc, sb.ac, d.Cp}, s));
-    MFAC_OK(gemm_fwd(sb.gc, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, EpiLinearBf16{bias + d.b_c2, sb.m, d.Mp}, s));
+    MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, bias + d.b_c1, sb.gc, sb.ac, d.Cp, s));
+    MFAC_OK(gemm_linear_bf16(sb.gc, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, bias + d.b_c2, sb.m, d.Mp, s));
     MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiMulDgelu{sb.ac, p.gcd, d.Cp}, s));
-    MFAC_OK(gemm_fwd(p.gcd, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, EpiLinearBf16{nullptr, p.md, d.Mp}, s));
+    MFAC_OK(gemm_linear_bf16(p.gcd, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
     LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd, d.Mp};
     MFAC_OK(lnmod(true, la, d, B, s));
-    MFAC_OK(gemm_fwd(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiBiasGelu{bias + d.b_m1, sb.g, sb.a, d.Ip}, s));
+    MFAC_OK(gemm_bias_gelu(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sb.g, sb.a, d.Ip, s));
     MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
     MFAC_OK(gemm_fwd(sb.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
                      EpiBlockOut{bias + d.b_m2, sb.m, x_in, x_out, sb.o, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));

@@ -608,6 +608,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 struct EpiGradStore {
   static constexpr const char* name = "grad_store";
   static constexpr int kPrefetchDepth = 0;  // store-only, rolled epilogue
+  static constexpr bool kTmaStore = false;
   float* G;       // leaf base in the flat gradient
   int ld;         // real number of columns
   int row_kind, row_limit, col_kind, col_limit;

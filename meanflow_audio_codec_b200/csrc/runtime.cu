@@ -75,8 +75,8 @@ int num_sms() {
   return n;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                   int box_outer) {
+int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer, int swizzle_bytes) {
   std::call_once(g_encode_once, resolve_encode);
   if (!g_encode) return MFAC_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return MFAC_ERR_UNSUPPORTED;
@@ -84,10 +84,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t out
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MFAC_SUCCESS : MFAC_ERR_DRIVER;
+}
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                   int box_outer) {
+  return make_tmap_bf16_sw(out, ptr, inner, outer, ld, box_inner, box_outer, 128);
 }
 
 }  // namespace mfac
