@@ -381,6 +381,195 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  A 2-wide cluster owns a 256 x 256 output tile: each CTA stages its own 128 rows of A
+// and HALF of the B tile (128 of the 256 columns), the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256)
+// which reads both CTAs' shared memory and writes each CTA's 128 x 256 accumulator into its own TMEM, and each CTA runs
+// the usual epilogue on its half.  Per SM this halves the B-operand fill and read traffic (32 instead of 48 KB per
+// k-block: six stages instead of four) -- the compute-bound GEMMs were limited by operand delivery, not by the tensor
+// pipe.  Protocol (after CUTLASS's sm100 2-SM pipeline):
+//   full[s]   lives in the leader; the leader's producer arms it with the pair's byte count, both CTAs' TMA loads
+//             complete_tx on it (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address)
+//   empty[s]  one per CTA; tcgen05.commit.cta_group::2 ... multicast arrives on both when the stage's MMAs retire
+//   tfull[a]  one per CTA, same multicast commit: the accumulator of buffer a is complete in both TMEMs
+//   tempty[a] lives in the leader and counts the epilogue warps of BOTH CTAs (the peer's arrive remotely)
+// ---------------------------------------------------------------------------------------
+constexpr int GEMM2_BN = 256;
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // this CTA's 128 rows
+  static constexpr int B_BYTES = (GEMM2_BN / 2) * GEMM_BK * 2;   // this CTA's 128 of the 256 columns
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * GEMM2_BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+  static_assert(STAGES * STAGE_BYTES + STAGING_BYTES <= GEMM_SMEM_TOTAL, "shared memory budget");
+};
+
+template <bool A_MN, bool B_MN, bool FULL, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape,
+                         Epi epi) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = GEMM2_BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = ceil_div(shape.M, 2 * GEMM_BM);  // 256-row pair tiles
+  const int n_tiles = ceil_div(shape.N, BN);
+  const int k_blocks_total = ceil_div(shape.K, GEMM_BK);
+  const int num_items = m_tiles * n_tiles * shape.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);   // both CTAs' epilogue warps (only the leader's copy is used)
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();                                // barriers of both CTAs initialised before any remote access
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
+    if (lane == 0) {
+      uint32_t kit = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const int tile = item / shape.splits, sp = item % shape.splits;
+        const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;   // this CTA's rows
+        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);           // this CTA's half of the columns
+        const int kb0 = sp * shape.kb_per_split;
+        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t lbar = mapa_u32(&full_bar[s], 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          uint8_t* a = sA + s * Cfg::A_BYTES;
+          uint8_t* b = sB + s * Cfg::B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair(a + j * 8192, &tmA, lbar, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(a, &tmA, lbar, k0, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 2 / 64; ++j) tma_load_2d_pair(b + j * 8192, &tmB, lbar, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(b, &tmB, lbar, k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, A_MN, B_MN);
+      uint32_t kit = 0, it = 0;
+      for (int item = pair; item < num_items; item += npairs, ++it) {
+        const int sp = item % shape.splits;
+        const int kb0 = sp * shape.kb_per_split;
+        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
+        const uint32_t as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+            const uint64_t ad = A_MN ? umma_smem_desc_sw128(a_addr + kk * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+            const uint64_t bd = B_MN ? umma_smem_desc_sw128(b_addr + kk * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
+            umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s]);   // both CTAs' stage s reusable once these MMAs retire
+        }
+        umma_commit_pair(&tfull_bar[as]);    // accumulator complete in both TMEMs
+      }
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
+  } else {
+    // ===================== epilogue (warps 4..11 of both CTAs) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_EPI));
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int etid = threadIdx.x - 128;
+    float4* st = reinterpret_cast<float4*>(sStage + (warp - 4) * 4096);
+    uint32_t it = 0;
+    const uint32_t lead_tempty0 = mapa_u32(&tempty_bar[0], 0), lead_tempty1 = mapa_u32(&tempty_bar[1], 0);
+    if (pair < num_items) {
+      const int tile = pair / shape.splits;
+      epi.prefetch((tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
+    }
+    for (int item = pair; item < num_items; item += npairs, ++it) {
+      const int tile = item / shape.splits;
+      const uint32_t as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      if (item + npairs < num_items) {
+        const int nt = (item + npairs) / shape.splits;
+        if (nt != tile)
+          epi.prefetch((nt / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
+      }
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
+      epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(as ? lead_tempty1 : lead_tempty0);
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while its partner can still read its shared memory or signal its barriers
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // Debug/triage kernel: same contract and epilogues, plain SIMT fp32 accumulation.
 // Selected only through mfac_debug_set_simt_gemm(1); never part of a product path.
 struct SimtOperand {
@@ -486,6 +675,69 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   return launch_status();
 }
 
+bool pair_gemm_enabled();   // runtime.cu: on unless MFAC_NO_PAIR_GEMM is set / mfac_debug_set_pair_gemm(0)
+
+// CTA pairs pay for compute-bound shapes that fill the machine with whole 256 x 256 tiles.
+inline bool pair_gemm_pays(int M, int N, int K, bool split_k) {
+  if (N % GEMM2_BN != 0 || M < 2 * GEMM_BM || K < 512) return false;
+  const int items = ceil_div(M, 2 * GEMM_BM) * (N / GEMM2_BN);
+  const int pairs = num_sms() / 2;
+  if (split_k) return items * 4 >= pairs;            // the split search below fills the waves
+  const double waves = (double)items / pairs;
+  return items >= pairs && waves / std::ceil(waves) >= 0.8;
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi, cudaStream_t stream,
+                     bool split_k) {
+  using Cfg = Gemm2Cfg;
+  CUtensorMap tmA, tmB;
+  if (A_MN) {
+    MFAC_OK(make_tmap_bf16(&tmA, A.ptr, M, K, A.ld, 64, 64));
+  } else {
+    MFAC_OK(make_tmap_bf16(&tmA, A.ptr, K, M, A.ld, 64, GEMM_BM));
+  }
+  if (B_MN) {
+    MFAC_OK(make_tmap_bf16(&tmB, B.ptr, N, K, B.ld, 64, 64));
+  } else {
+    MFAC_OK(make_tmap_bf16(&tmB, B.ptr, K, N, B.ld, 64, GEMM2_BN / 2));
+  }
+  const bool full = (M % (2 * GEMM_BM) == 0) && (N % GEMM2_BN == 0);
+  auto kern = full ? gemm_tcgen05_pair_kernel<A_MN, B_MN, true, Epi> : gemm_tcgen05_pair_kernel<A_MN, B_MN, false, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<A_MN, B_MN, true, Epi>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<A_MN, B_MN, false, Epi>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, GEMM2_BN);
+  const int k_blocks = ceil_div(K, GEMM_BK);
+  const int pairs = num_sms() / 2;
+  int splits = 1;
+  if (split_k) {
+    double best = -1.0;
+    for (int sp = 1; sp <= 32 && sp <= k_blocks; ++sp) {
+      if (sp > 1 && k_blocks / sp < 4) break;
+      const int items = tiles * ceil_div(k_blocks, ceil_div(k_blocks, sp));
+      const double waves = (double)items / pairs;
+      const double eff = waves / std::ceil(waves) - 0.004 * sp;
+      if (eff > best) { best = eff; splits = sp; }
+    }
+  }
+  const int kbps = ceil_div(k_blocks, splits);
+  splits = ceil_div(k_blocks, kbps);
+  const int items = tiles * splits;
+  const int grid = 2 * (items < pairs ? items : pairs);
+  GemmShape shape{M, N, K, splits, kbps};
+  void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
+  profile_end(prof, stream);
+  count_launch();
+  return launch_status();
+}
+
 // C = A * B with the given epilogue.  N must be a multiple of 4; K and M are arbitrary
 // (TMA zero-fills), leading dimensions must be multiples of 8 elements (16-byte TMA strides).
 // split_k = true lets the launcher slice K so that (tiles x slices) covers the machine; the epilogue
@@ -532,6 +784,9 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
       const double eff = waves / std::ceil(waves) - 0.004 * sp;  // mild preference for fewer atomics
       if (eff > best) { best = eff; splits = sp; }
     }
+  }
+  if constexpr (!Epi::kTmaStore) {
+    if (!force_bn && pair_gemm_enabled() && pair_gemm_pays(M, N, K, split_k)) return launch_gemm_pair<A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, split_k);
   }
   if (bn == 256) return launch_gemm_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);
   return launch_gemm_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);
