@@ -981,7 +981,9 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
         const double eff = (waves / std::ceil(waves)) * ((double)S / (S + 3));
         if (eff > best + 1e-9) { best = eff; best_S = S; }
       }
+      if (const char* e = getenv("MFAC_IMDCT_S")) best_S = atoi(e) > 0 ? atoi(e) : best_S;   // tuning hook
       const int spc = (int)ceil_div<int64_t>(nblocks, best_S);
+      best_S = (int)ceil_div<int64_t>(nblocks, spc);   // same stream count, balanced stream lengths
       const int64_t total = B * (int64_t)spc;
       imdct512h256_stream_kernel<<<(unsigned)ceil_div<int64_t>(total, F2_THREADS / 16), F2_THREADS, S2_SMEM, stream>>>(
           X, y, ts.fft, nf, io.in_clip_stride, io.out_clip_stride, best_S, spc, total);
