@@ -142,6 +142,12 @@ typedef struct MfacImfAux {
   float* e;           /* [B,D] noise actually used */
   float* t;           /* [B] */
   float* r;           /* [B] */
+  /* Optional host callback, invoked on the calling thread right after the launches that finalise the gradient
+   * slice grads[offset, offset+count) have been enqueued on `stream` (blocks nb-1 .. 0, then the encoder).  A
+   * data-parallel caller starts that bucket's all-reduce from it, so the exchange overlaps the rest of the backward
+   * (the reference has no distributed code). */
+  void (*grad_ready)(void* user, int64_t offset, int64_t count);
+  void* grad_ready_user;
 } MfacImfAux;
 
 MFAC_API int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,

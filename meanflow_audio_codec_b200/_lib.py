@@ -31,8 +31,12 @@ class ImfConfig(C.Structure):
     ]
 
 
+GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
+
+
 class ImfAux(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("v", "u", "dudt", "per_example", "e", "t", "r")]
+    _fields_ = ([(n, C.c_void_p) for n in ("v", "u", "dudt", "per_example", "e", "t", "r")] +
+                [("grad_ready", GRAD_READY_FN), ("grad_ready_user", C.c_void_p)])
 
 
 class Dense(C.Structure):

@@ -416,6 +416,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
     MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, 1, d}, s));
     MFAC_OK(colsum(p.g_ac, d.Cp, B, gk + d.o_c1b, MAP_ID, d.C, d, s));
+    if (aux && aux->grad_ready) aux->grad_ready(aux->grad_ready_user, (int64_t)k * d.blk_stride, d.blk_stride);
   }
   // ---- encoder backward
   f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);
@@ -425,6 +426,8 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, s));
   MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, 1, d}, s));
   MFAC_OK(colsum(p.g_ae, d.Hep, B, grads + d.o_e1b, MAP_ID, d.He, d, s));
+  if (aux && aux->grad_ready)
+    aux->grad_ready(aux->grad_ready_user, (int64_t)d.nb * d.blk_stride, d.total - (int64_t)d.nb * d.blk_stride);
   // ---- optional intermediates for parity tests
   if (aux) {
     const unsigned nbk = blocks_for(B * d.D, 256);

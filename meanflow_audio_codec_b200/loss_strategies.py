@@ -73,8 +73,11 @@ class ImprovedMeanFlowLoss(LossStrategy):
                               None if step_dev is None else step_dev.data_ptr())
 
     def compute_loss(self, state: TrainState, key, x, *, noise=None, t=None, r=None, step: int | None = None,
-                     row_offset: int = 0, return_aux: bool = False, step_tensor=None):
-        """``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay)."""
+                     row_offset: int = 0, return_aux: bool = False, step_tensor=None, grad_ready=None):
+        """``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay).
+        ``grad_ready(flat_slice)``: optional host callback, called as soon as the launches that finalise a slice of the
+        flat gradient are enqueued (block by block, last block first, encoder last) -- data_parallel.py starts that
+        bucket's all-reduce from it."""
         model: ConditionalFlow = state.model
         fp = model.flat_params(state.params)
         x = _lib.require_cuda(x, "x").to(torch.float32).contiguous()
@@ -95,6 +98,10 @@ class ImprovedMeanFlowLoss(LossStrategy):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         grads = torch.empty_like(fp.flat)
         aux_t, aux = {}, None
+        cb_keep = None
+        if grad_ready is not None and not return_aux:
+            cb_keep = _lib.GRAD_READY_FN(lambda user, off, cnt: grad_ready(grads[off:off + cnt]))
+            aux = _lib.ImfAux(*([None] * 7), cb_keep, None)
         if return_aux:
             D = model.noise_dimension
             aux_t = {k: torch.empty((B, D), dtype=torch.float32, device=dev) for k in ("v", "u", "dudt", "e")}
