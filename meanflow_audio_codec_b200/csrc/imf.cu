@@ -113,7 +113,7 @@ int ln_bwd(const LnBwdArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
 struct FwdScratch {
   __nv_bfloat16 *gc, *m, *hin, *g;
   void plan(Arena& ar, const Dims& d, int64_t B) {
-    gc = ar.take<__nv_bfloat16>(B * d.Cp);
+    gc = ar.take<__nv_bfloat16>(B * d.Ca);   // first modulation layer of all blocks: [B, nb*Cp]
     m = ar.take<__nv_bfloat16>(B * d.Mp);
     hin = ar.take<__nv_bfloat16>(B * d.Ip);
     g = ar.take<__nv_bfloat16>(B * d.Ip);
@@ -130,11 +130,12 @@ int forward_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* cond, con
   const int Mc = uniform_cond ? 1 : M;
   const int64_t m_stride = uniform_cond ? 0 : d.Mp;
   const float inv_nb = 1.0f / (float)d.nb;
+  // first modulation layer of ALL blocks in one GEMM (they share the input row `cond`)
+  MFAC_OK(gemm_bias_gelu(cond, d.Cp, sh.w + d.s_c1all, Mc, d.Ca, d.Cp, sh.b + d.b_c1all, sc.gc, nullptr, d.Ca, s));
   for (int k = 0; k < d.nb; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
-    MFAC_OK(gemm_bias_gelu(cond, d.Cp, w + d.s_c1w, Mc, d.Cp, d.Cp, bias + d.b_c1, sc.gc, nullptr, d.Cp, s));
-    MFAC_OK(gemm_linear_bf16(sc.gc, d.Cp, w + d.s_c2w, Mc, d.Mp, d.Cp, bias + d.b_c2, sc.m, d.Mp, s));
+    MFAC_OK(gemm_linear_bf16(sc.gc + k * d.Cp, d.Ca, w + d.s_c2w, Mc, d.Mp, d.Cp, bias + d.b_c2, sc.m, d.Mp, s));
     LnModArgs la{lat, x, sc.m, sc.hin, nullptr, nullptr, nullptr, nullptr, nullptr, m_stride};
     MFAC_OK(lnmod(false, la, d, B, s));
     MFAC_OK(gemm_bias_gelu(sc.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sc.g, nullptr, d.Ip, s));
@@ -182,7 +183,8 @@ struct LossGradPlan {
   float* xs;  // [(nb+1), B, Dp]
   SavedBlock blk[64];
   // tangent transients
-  __nv_bfloat16 *gcd, *md, *hind, *gd;
+  __nv_bfloat16 *gcd, *md, *hind, *gd;   // gcd: [B, nb*Cp]
+  __nv_bfloat16 *ac_all, *gc_all;        // [B, nb*Cp]: pre-activation / activation of the batched first modulation layer
   float* xd;
   // loss / backward
   float *row_loss, *g_x, *g_lat;
@@ -203,10 +205,12 @@ struct LossGradPlan {
     v = ar.take<float>(B * d.Dp);
     fs.plan(ar, d, B);
     xs = ar.take<float>((int64_t)(d.nb + 1) * B * d.Dp);
+    ac_all = ar.take<__nv_bfloat16>(B * d.Ca);
+    gc_all = ar.take<__nv_bfloat16>(B * d.Ca);
     for (int k = 0; k < d.nb; ++k) {
       SavedBlock& sb = blk[k];
-      sb.ac = ar.take<__nv_bfloat16>(B * d.Cp);
-      sb.gc = ar.take<__nv_bfloat16>(B * d.Cp);
+      sb.ac = ac_all ? ac_all + k * d.Cp : nullptr;   // column slices of the batched [B, nb*Cp] tensors (ld = Ca)
+      sb.gc = gc_all ? gc_all + k * d.Cp : nullptr;
       sb.m = ar.take<__nv_bfloat16>(B * d.Mp);
       sb.hin = ar.take<__nv_bfloat16>(B * d.Ip);
       sb.a = ar.take<__nv_bfloat16>(B * d.Ip);
@@ -215,7 +219,7 @@ struct LossGradPlan {
       sb.mu = ar.take<float>(B);
       sb.rstd = ar.take<float>(B);
     }
-    gcd = ar.take<__nv_bfloat16>(B * d.Cp);
+    gcd = ar.take<__nv_bfloat16>(B * d.Ca);
     md = ar.take<__nv_bfloat16>(B * d.Mp);
     hind = ar.take<__nv_bfloat16>(B * d.Ip);
     gd = ar.take<__nv_bfloat16>(B * d.Ip);
@@ -226,7 +230,7 @@ struct LossGradPlan {
     g_o = ar.take<__nv_bfloat16>(B * d.Dp);
     g_a = ar.take<__nv_bfloat16>(B * d.Ip);
     g_m = ar.take<__nv_bfloat16>(B * d.Mp);
-    g_ac = ar.take<__nv_bfloat16>(B * d.Cp);
+    g_ac = ar.take<__nv_bfloat16>(B * d.Ca);
     g_latb = ar.take<__nv_bfloat16>(B * d.Lp);
     g_ae = ar.take<__nv_bfloat16>(B * d.Hep);
   }
@@ -362,6 +366,9 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
   // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
   MFAC_CUDA_OK(cudaMemcpyAsync(p.xs, p.z, row_bytes, cudaMemcpyDeviceToDevice, s));
+  // first modulation layer of all blocks, primal and tangent, in two GEMMs
+  MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
+  MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
   for (int k = 0; k < d.nb; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
@@ -370,10 +377,8 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp;
     const float* xd_in = k == 0 ? p.v : p.xd;
     // modulation, primal and tangent
-    MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, bias + d.b_c1, sb.gc, sb.ac, d.Cp, s));
-    MFAC_OK(gemm_linear_bf16(sb.gc, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, bias + d.b_c2, sb.m, d.Mp, s));
-    MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, w + d.s_c1w, M, d.Cp, d.Cp, EpiMulDgelu{sb.ac, p.gcd, d.Cp}, s));
-    MFAC_OK(gemm_linear_bf16(p.gcd, d.Cp, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
+    MFAC_OK(gemm_linear_bf16(sb.gc, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, bias + d.b_c2, sb.m, d.Mp, s));
+    MFAC_OK(gemm_linear_bf16(p.gcd + k * d.Cp, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
     LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd, d.Mp};
     MFAC_OK(lnmod(true, la, d, B, s));
     MFAC_OK(gemm_bias_gelu(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sb.g, sb.a, d.Ip, s));
@@ -410,13 +415,18 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
-    MFAC_OK(gemm_dw(sb.gc, d.Cp, p.g_m, d.Mp, d.Cp, d.Mp, M,
+    MFAC_OK(gemm_dw(sb.gc, d.Ca, p.g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
     MFAC_OK(colsum(p.g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, s, 2 * d.Ip));  // s1 | shift thirds
-    MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac, d.Cp}, s));
-    MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Cp, d.Cp, d.Cp, M, EpiGradStore{gk + d.o_c1w, d.C, MAP_ID, d.C, MAP_ID, d.C, 1, d}, s));
-    MFAC_OK(colsum(p.g_ac, d.Cp, B, gk + d.o_c1b, MAP_ID, d.C, d, s));
-    if (aux && aux->grad_ready) aux->grad_ready(aux->grad_ready_user, (int64_t)k * d.blk_stride, d.blk_stride);
+    MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac + k * d.Cp, d.Ca}, s));
+    if (k == 0) {
+      // first modulation layer, all blocks at once: dW = cond^T @ g_ac_all, db = column sums
+      MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Ca, d.Cp, d.Ca, M, EpiGradStoreC1{grads, d}, s));
+      MFAC_OK(colsum(p.g_ac, d.Ca, B, grads, MAP_C1ALL, 0, d, s));
+    }
+    // with the batched cond1 gradients every block's slice is only final after block 0; buckets are announced then
+    if (aux && aux->grad_ready && k == 0)
+      for (int kk = d.nb - 1; kk >= 0; --kk) aux->grad_ready(aux->grad_ready_user, (int64_t)kk * d.blk_stride, d.blk_stride);
   }
   // ---- encoder backward
   f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);

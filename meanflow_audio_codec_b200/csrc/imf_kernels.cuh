@@ -358,7 +358,7 @@ __global__ void f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t
 
 // padded -> real column maps of the flat (Flax-order) gradient
 constexpr int COLSUM_VROWS = 256;
-enum ColMap { MAP_ID = 0, MAP_CM = 1, MAP_MM = 2 };
+enum ColMap { MAP_ID = 0, MAP_CM = 1, MAP_MM = 2, MAP_C1ALL = 3 };
 __device__ __forceinline__ int map_col(int kind, int p, int limit, const Dims& d) {
   if (kind == MAP_CM) return d.cm_inv(p);
   if (kind == MAP_MM) return d.mm_inv(p);
@@ -595,8 +595,13 @@ __global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloa
     float sum = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) sum += s_red[q][threadIdx.x];
-    const int oc = map_col(kind, c, limit, d);
-    if (oc >= 0) atomicAdd(out + oc, sum);
+    if (kind == MAP_C1ALL) {   // batched cond1 bias: column k*Cp + cc of [B, nb*Cp] -> block k's cond1.bias[cc]
+      const int k = c / d.Cp, cc = c - k * d.Cp;
+      if (cc < d.C) atomicAdd(out + (int64_t)k * d.blk_stride + d.o_c1b + cc, sum);
+    } else {
+      const int oc = map_col(kind, c, limit, d);
+      if (oc >= 0) atomicAdd(out + oc, sum);
+    }
   }
 }
 
@@ -638,6 +643,35 @@ struct EpiGradStore {
           else dst[c] = v[j];
         }
       }
+    }
+  }
+};
+
+
+// Weight gradient of the batched first modulation layer: (row r, column k*Cp + c) of cond^T @ g_ac_all -> block k's
+// cond1.kernel[r, c] in the flat gradient.  Split-K partials accumulate with red.global.add.
+struct EpiGradStoreC1 {
+  static constexpr const char* name = "grad_store";
+  static constexpr int kPrefetchDepth = 0;
+  static constexpr bool kTmaStore = false;
+  float* grads;   // flat gradient base
+  Dims d;
+  using Regs = NoRegs;
+  using ColRegs = NoRegs;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int, ColRegs&) const {}
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs&) const {
+    if (row >= d.C) return;
+    const int k = col / d.Cp, c = col - k * d.Cp;
+    float* dst = grads + (int64_t)k * d.blk_stride + d.o_c1w + (int64_t)row * d.C + c;
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (c + 3 < d.C && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      red_add_v4(dst, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < d.C) atomicAdd(dst + j, v[j]);
     }
   }
 };

@@ -23,13 +23,16 @@ struct Dims {
   int D, L, C, nb;
   int I, He;
   int Dp, Lp, Cp, Ip, Hep, Mp;
+  int Ca;  // nb * Cp: width of the batched first modulation layer (all blocks' cond1 kernels side by side)
   // flat parameter offsets inside one block, the block stride, and the encoder base
   int64_t o_c1b, o_c1w, o_c2b, o_c2w, o_m1b, o_m1w, o_m2b, o_m2w, blk_stride;
   int64_t o_e1b, o_e1w, o_e2b, o_e2w, total;
   // bf16 shadow offsets (elements) inside one block, block stride, encoder offsets, total
-  int64_t s_c1w, s_c2w, s_m1w, s_m2w, s_blk_stride, s_e1w, s_e2w, s_total;
+  // The cond1 kernels of ALL blocks form one [Cp, nb*Cp] matrix at s_c1all (block k = columns [k*Cp, (k+1)*Cp)): every
+  // block's first modulation layer sees the same input row, so one GEMM evaluates them all.
+  int64_t s_c2w, s_m1w, s_m2w, s_blk_stride, s_e1w, s_e2w, s_c1all, s_total;
   // padded fp32 bias offsets (elements) inside the bias section of the shadow
-  int64_t b_c1, b_c2, b_m1, b_m2, b_blk_stride, b_e1, b_e2, b_total;
+  int64_t b_c2, b_m1, b_m2, b_blk_stride, b_e1, b_e2, b_c1all, b_total;
   int64_t bias_section_bytes_offset;  // byte offset of the fp32 bias section inside the shadow buffer
 
   __host__ __device__ int cm(int j) const { return j < L ? j : Lp + (j - L); }
@@ -68,6 +71,7 @@ inline int make_dims(const MfacMlpDims* d, Dims* out) {
   x.Dp = round_up(x.D, 64); x.Lp = round_up(x.L, 64); x.Cp = round_up(x.C, 64); x.Hep = round_up(x.He, 64);
   x.Ip = x.Lp + x.Dp;
   x.Mp = 2 * x.Ip + x.Dp;
+  x.Ca = x.nb * x.Cp;
   const int64_t I = x.I, D = x.D, C = x.C, L = x.L, He = x.He;
   int64_t o = 0;
   x.o_c1b = o; o += C;
@@ -87,7 +91,6 @@ inline int make_dims(const MfacMlpDims* d, Dims* out) {
   x.total = o;
   int64_t s = 0;
   auto take = [&](int64_t n) { int64_t at = s; s += round_up<int64_t>(n, 128); return at; };
-  x.s_c1w = take((int64_t)x.Cp * x.Cp);
   x.s_c2w = take((int64_t)x.Cp * x.Mp);
   x.s_m1w = take((int64_t)x.Ip * x.Ip);
   x.s_m2w = take((int64_t)x.Ip * x.Dp);
@@ -95,10 +98,10 @@ inline int make_dims(const MfacMlpDims* d, Dims* out) {
   s = x.s_blk_stride * x.nb;
   x.s_e1w = take((int64_t)x.Dp * x.Hep);
   x.s_e2w = take((int64_t)x.Hep * x.Lp);
+  x.s_c1all = take((int64_t)x.Cp * x.Ca);
   x.s_total = s;
   int64_t bo = 0;
   auto takeb = [&](int64_t n) { int64_t at = bo; bo += round_up<int64_t>(n, 64); return at; };
-  x.b_c1 = takeb(x.Cp);
   x.b_c2 = takeb(x.Mp);
   x.b_m1 = takeb(x.Ip);
   x.b_m2 = takeb(x.Dp);
@@ -106,6 +109,7 @@ inline int make_dims(const MfacMlpDims* d, Dims* out) {
   bo = x.b_blk_stride * x.nb;
   x.b_e1 = takeb(x.Hep);
   x.b_e2 = takeb(x.Lp);
+  x.b_c1all = takeb(x.Ca);
   x.b_total = bo;
   x.bias_section_bytes_offset = round_up<int64_t>(x.s_total * 2, 256);
   *out = x;
@@ -123,11 +127,11 @@ __host__ __device__ inline ShadowSlot shadow_slot_of(const Dims& d, int64_t i) {
     const int64_t k = i / d.blk_stride;
     const int64_t w = i - k * d.blk_stride;
     const int64_t base_s = k * d.s_blk_stride, base_b = k * d.b_blk_stride;
-    if (w < d.o_c1w) return {base_b + d.b_c1 + (w - d.o_c1b), true};
+    if (w < d.o_c1w) return {d.b_c1all + k * d.Cp + (w - d.o_c1b), true};
     if (w < d.o_c2b) {
       const int64_t q = w - d.o_c1w;
       const uint32_t qq = (uint32_t)q; const int r = (int)(qq / (uint32_t)d.C), c = (int)(qq % (uint32_t)d.C);
-      return {base_s + d.s_c1w + (int64_t)r * d.Cp + c, false};
+      return {d.s_c1all + (int64_t)r * d.Ca + k * d.Cp + c, false};
     }
     if (w < d.o_c2w) return {base_b + d.b_c2 + d.mm((int)(w - d.o_c2b)), true};
     if (w < d.o_m1b) {
