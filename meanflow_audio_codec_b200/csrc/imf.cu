@@ -171,7 +171,7 @@ struct SavedBlock {
 
 struct LossGradPlan {
   // prologue
-  float *e, *z, *t, *r;
+  float *e, *t, *r;
   __nv_bfloat16 *xb, *cond_v, *cond_u, *dcond_u;
   // encoder
   __nv_bfloat16 *a_e, *g_e;
@@ -192,7 +192,6 @@ struct LossGradPlan {
 
   void plan(Arena& ar, const Dims& d, int64_t B) {
     e = ar.take<float>(B * d.Dp);
-    z = ar.take<float>(B * d.Dp);
     t = ar.take<float>(B);
     r = ar.take<float>(B);
     xb = ar.take<__nv_bfloat16>(B * d.Dp);
@@ -353,19 +352,16 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   Shadow sh(shadow, d);
   const int M = (int)B;
   const float inv_nb = 1.0f / (float)d.nb;
-  const size_t row_bytes = (size_t)B * d.Dp * 4;
 
   // ---- prologue: (e, t, r), z_t, cond rows
-  PrepArgs pa{x, e, t, r, p.e, p.z, p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};
+  PrepArgs pa{x, e, t, r, p.e, p.v, p.xs, p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};   // z_t -> v and xs[0]
   imf_prep_kernel<<<(unsigned)B, ROW_THREADS, 0, s>>>(pa, d);
   count_launch();
   // ---- latents = encode(x)
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
   // ---- v = f(z, [t, 0], lat)
-  MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.z, row_bytes, cudaMemcpyDeviceToDevice, s));
   MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
   // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
-  MFAC_CUDA_OK(cudaMemcpyAsync(p.xs, p.z, row_bytes, cudaMemcpyDeviceToDevice, s));
   // first modulation layer of all blocks, primal and tangent, in two GEMMs
   MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
   MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));

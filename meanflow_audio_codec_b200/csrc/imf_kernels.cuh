@@ -87,7 +87,8 @@ struct PrepArgs {
   const float* t_in;   // [B] or null
   const float* r_in;   // [B] or null
   float* e;            // [B, Dp]
-  float* z;            // [B, Dp]
+  float* z;            // [B, Dp]  z_t, written twice: the v pass and the u pass both start from it and update in place
+  float* z2;           // [B, Dp]
   __nv_bfloat16* xb;   // [B, Dp]
   float* t;            // [B]
   float* r;            // [B]
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
         e = a.e_in ? a.e_in[b * d.D + j] : ev[q];
       }
       a.e[b * d.Dp + j] = e;
-      a.z[b * d.Dp + j] = (1.0f - t) * xv + nscale * e;
+      const float zt = (1.0f - t) * xv + nscale * e;
+      a.z[b * d.Dp + j] = zt;
+      a.z2[b * d.Dp + j] = zt;
       a.xb[b * d.Dp + j] = __float2bfloat16(xv);
     }
   }
