@@ -132,7 +132,15 @@ typedef struct MfacImfConfig {
   uint64_t row_offset;                 /* global index of local row 0 (rank * B) for the RNG */
   const uint64_t* step_dev;            /* optional DEVICE counter read instead of `step` (CUDA-graph replay: the
                                           captured launch must see a step that advances); NULL = use `step` */
+  int32_t method;                      /* MfacLossMethod: which loss strategy (trainers/loss_strategies.py) */
+  float gamma;                         /* mean flow: adaptive weight 1 / (mean_D delta^2 + loss_c)^(1 - gamma) */
+  int32_t uniform_time;                /* 1: t ~ U(0,1) (UniformTimeSampling) instead of logit-normal, internal RNG only */
 } MfacImfConfig;
+
+/* ref: trainers/loss_strategies.py -- ImprovedMeanFlowLoss :204-280 (tangent seed = the network's own v),
+ * MeanFlowLoss :115-201 (z = (1-t)x + t e, tangent seed = e - x, adaptive weight; pass noise_min = 0, noise_max = 1),
+ * FlowMatchingLoss :50-112 (single time, h = 0, no JVP; r is ignored). */
+enum MfacLossMethod { MFAC_LOSS_IMPROVED_MEAN_FLOW = 0, MFAC_LOSS_MEAN_FLOW = 1, MFAC_LOSS_FLOW_MATCHING = 2 };
 
 typedef struct MfacImfAux {
   float* v;           /* [B,D] */

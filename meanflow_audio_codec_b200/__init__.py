@@ -9,8 +9,9 @@ from .mdct import MDCTConfig, MDCTLayer, IMDCTLayer, imdct, mdct  # noqa: F401
 from .tokenization import (MDCTTokenization, compute_token_shape, compute_tokenized_dimension,  # noqa: F401
                            create_tokenization_strategy)
 from .mlp_flow import AdamW, ConditionalFlow, TrainState, adamw  # noqa: F401
-from .loss_strategies import (ImprovedMeanFlowLoss, LinearNoiseSchedule, LossStrategy,  # noqa: F401
-                              MeanFlowTimeSampling, train_step)
+from .loss_strategies import (FlowMatchingLoss, ImprovedMeanFlowLoss, LinearNoiseSchedule,  # noqa: F401
+                              LogitNormalTimeSampling, LossStrategy, MeanFlowLoss, MeanFlowTimeSampling,
+                              UniformNoiseSchedule, UniformTimeSampling, create_loss_strategy, train_step)
 from .sampling import sample, sample_mean_flow  # noqa: F401
 from .graphs import GraphedTrainStep  # noqa: F401
 from .flows import ConditionalConvFlow, ConditionalMLPMixerFlow, create_flow_model  # noqa: F401

@@ -28,6 +28,7 @@ class ImfConfig(C.Structure):
         ("use_weighted_loss", C.c_int32),
         ("seed", C.c_uint64), ("step", C.c_uint64), ("row_offset", C.c_uint64),
         ("step_dev", C.c_void_p),
+        ("method", C.c_int32), ("gamma", C.c_float), ("uniform_time", C.c_int32),
     ]
 
 
@@ -114,6 +115,7 @@ PROTOTYPES = {
 }
 
 WS_FORWARD, WS_LOSS_GRAD, WS_SAMPLE = 0, 1, 2
+LOSS_IMPROVED_MEAN_FLOW, LOSS_MEAN_FLOW, LOSS_FLOW_MATCHING = 0, 1, 2
 SAMPLE_HEUN, SAMPLE_MF = 0, 1
 
 _lib = None

@@ -354,17 +354,22 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   const float inv_nb = 1.0f / (float)d.nb;
 
   // ---- prologue: (e, t, r), z_t, cond rows
-  PrepArgs pa{x, e, t, r, p.e, p.v, p.xs, p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};   // z_t -> v and xs[0]
+  if (cfg->method < MFAC_LOSS_IMPROVED_MEAN_FLOW || cfg->method > MFAC_LOSS_FLOW_MATCHING) return MFAC_ERR_UNSUPPORTED;
+  const bool need_v = cfg->method == MFAC_LOSS_IMPROVED_MEAN_FLOW;   // tangent seed = the network's own velocity
+  const bool tangent = cfg->method != MFAC_LOSS_FLOW_MATCHING;       // flow matching has no JVP
+  // z_t -> xs[0] (u pass) and, for improved mean flow, v (v pass, in place); mean flow seeds the tangent with e - x
+  PrepArgs pa{x, e, t, r, p.e, need_v ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
+              p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};
   imf_prep_kernel<<<(unsigned)B, ROW_THREADS, 0, s>>>(pa, d);
   count_launch();
   // ---- latents = encode(x)
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
   // ---- v = f(z, [t, 0], lat)
-  MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
+  if (need_v) MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
   // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
   // first modulation layer of all blocks, primal and tangent, in two GEMMs
   MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
-  MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
+  if (tangent) MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
   for (int k = 0; k < d.nb; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
@@ -374,19 +379,20 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     const float* xd_in = k == 0 ? p.v : p.xd;
     // modulation, primal and tangent
     MFAC_OK(gemm_linear_bf16(sb.gc, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, bias + d.b_c2, sb.m, d.Mp, s));
-    MFAC_OK(gemm_linear_bf16(p.gcd + k * d.Cp, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
+    if (tangent) MFAC_OK(gemm_linear_bf16(p.gcd + k * d.Cp, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
     LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd, d.Mp};
-    MFAC_OK(lnmod(true, la, d, B, s));
+    MFAC_OK(lnmod(tangent, la, d, B, s));
     MFAC_OK(gemm_bias_gelu(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sb.g, sb.a, d.Ip, s));
-    MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
+    if (tangent) MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
     MFAC_OK(gemm_fwd(sb.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
                      EpiBlockOut{bias + d.b_m2, sb.m, x_in, x_out, sb.o, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
-    MFAC_OK(gemm_fwd(p.gd, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
-                     EpiBlockOutTangent{sb.m, p.md, sb.o, xd_in, p.xd, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
+    if (tangent)
+      MFAC_OK(gemm_fwd(p.gd, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
+                       EpiBlockOutTangent{sb.m, p.md, sb.o, xd_in, p.xd, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
   }
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
   // ---- loss and its seed gradient
-  LossArgs lo{u, p.xd, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};
+  LossArgs lo{u, tangent ? p.xd : nullptr, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};
   imf_loss_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Dp * 4, s>>>(lo, d);
   count_launch();
   sum_rows_kernel<<<1, 1024, 0, s>>>(p.row_loss, B, loss);
@@ -437,9 +443,9 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   // ---- optional intermediates for parity tests
   if (aux) {
     const unsigned nbk = blocks_for(B * d.D, 256);
-    if (aux->v) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.v, d.Dp, aux->v, d.D, B); count_launch(); }
+    if (aux->v && need_v) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.v, d.Dp, aux->v, d.D, B); count_launch(); }
     if (aux->u) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(u, d.Dp, aux->u, d.D, B); count_launch(); }
-    if (aux->dudt) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.xd, d.Dp, aux->dudt, d.D, B); count_launch(); }
+    if (aux->dudt && tangent) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.xd, d.Dp, aux->dudt, d.D, B); count_launch(); }
     if (aux->e) { unpad_rows_kernel<<<nbk, 256, 0, s>>>(p.e, d.Dp, aux->e, d.D, B); count_launch(); }
     if (aux->t) MFAC_CUDA_OK(cudaMemcpyAsync(aux->t, p.t, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
     if (aux->r) MFAC_CUDA_OK(cudaMemcpyAsync(aux->r, p.r, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));

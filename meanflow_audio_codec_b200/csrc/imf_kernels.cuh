@@ -87,8 +87,9 @@ struct PrepArgs {
   const float* t_in;   // [B] or null
   const float* r_in;   // [B] or null
   float* e;            // [B, Dp]
-  float* z;            // [B, Dp]  z_t, written twice: the v pass and the u pass both start from it and update in place
-  float* z2;           // [B, Dp]
+  float* z;            // [B, Dp] or null  z_t for the v pass (improved mean flow only), updated in place by it
+  float* z2;           // [B, Dp]  z_t for the u pass
+  float* seed;         // [B, Dp] or null  tangent seed noise_max e - x (mean flow: the JVP runs along the true velocity)
   __nv_bfloat16* xb;   // [B, Dp]
   float* t;            // [B]
   float* r;            // [B]
@@ -108,12 +109,15 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
       r = a.r_in[b];
     } else {
       const float4 n4 = philox_normal4(a.cfg.row_offset + b, 1u, a.cfg.seed, step);
-      const float lt = 1.0f / (1.0f + expf(-(n4.x * a.cfg.time_std + a.cfg.time_mean)));
+      float lt = 1.0f / (1.0f + expf(-(n4.x * a.cfg.time_std + a.cfg.time_mean)));
       const float lr = 1.0f / (1.0f + expf(-(n4.y * a.cfg.time_std + a.cfg.time_mean)));
+      if (a.cfg.uniform_time) lt = 0.5f * (1.0f + erff(n4.x * 0.70710678118654752f));  // Phi(N(0,1)) ~ U(0,1)
       t = fmaxf(lt, lr);
       r = fminf(lt, lr);
       if (b < (int64_t)((float)a.B * a.cfg.data_proportion)) r = t;  // utils.py:41-44, per local shard
+      if (a.cfg.method == MFAC_LOSS_FLOW_MATCHING) t = lt;           // a single time (time_sampling.py:44-75)
     }
+    if (a.cfg.method == MFAC_LOSS_FLOW_MATCHING) r = t;               // h = 0 (loss_strategies.py:88)
     s_tr[0] = t; s_tr[1] = r;
     a.t[b] = t; a.r[b] = r;
   }
@@ -137,12 +141,13 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
       }
       a.e[b * d.Dp + j] = e;
       const float zt = (1.0f - t) * xv + nscale * e;
-      a.z[b * d.Dp + j] = zt;
+      if (a.z) a.z[b * d.Dp + j] = zt;
       a.z2[b * d.Dp + j] = zt;
+      if (a.seed) a.seed[b * d.Dp + j] = a.cfg.noise_max * e - xv;
       a.xb[b * d.Dp + j] = __float2bfloat16(xv);
     }
   }
-  write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + b * d.Cp, nullptr);
+  if (a.z) write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + b * d.Cp, nullptr);
   write_cond_row(t, t - r, d.C, d.Cp, a.cond_u + b * d.Cp, a.dcond_u + b * d.Cp);
 }
 
@@ -268,13 +273,15 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
   extern __shared__ float s_delta[];  // [Dp]
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
-  const float tr = a.t[b] - a.r[b];
+  // MeanFlowLoss clips (t - r) to [0, 1] (loss_strategies.py:178); ImprovedMeanFlowLoss does not (:270)
+  float tr = a.t[b] - a.r[b];
+  if (a.cfg.method == MFAC_LOSS_MEAN_FLOW) tr = fminf(fmaxf(tr, 0.f), 1.f);
   float sq = 0.f;
   for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) {
     float dl = 0.f;
     if (j < d.D) {
       const int64_t i = b * d.Dp + j;
-      const float vpred = a.u[i] + tr * a.dudt[i];
+      const float vpred = a.dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
       dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
     }
     s_delta[j] = dl;
@@ -282,7 +289,13 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
   }
   const float s = block_sum(sq, red);
   float w, rl;
-  if (a.cfg.use_weighted_loss) {
+  if (a.cfg.method == MFAC_LOSS_MEAN_FLOW) {
+    // adaptive reweighting: w = 1 / (mean_D delta^2 + c)^(1 - gamma), loss = mean_B(w mean_D delta^2)
+    const float dsq = s / (float)d.D;
+    w = powf(dsq + a.cfg.loss_c, -(1.0f - a.cfg.gamma));
+    rl = w * dsq / (float)a.B;
+    w = 2.0f * w / ((float)d.D * (float)a.B);
+  } else if (a.cfg.use_weighted_loss) {
     w = 1.0f / (s + a.cfg.loss_c);
     rl = w * s / (float)a.B;
     w = 2.0f * w / (float)a.B;

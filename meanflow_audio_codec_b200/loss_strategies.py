@@ -1,9 +1,10 @@
 """Host-side mirror of trainers/{loss_strategies,noise_schedules,time_sampling,training_steps}.py for the
 iMF path, dispatching to the fused CUDA step (``mfac_imf_loss_grad``).
 
-ref: LossStrategy trainers/loss_strategies.py:27-47; ImprovedMeanFlowLoss :204-280;
-LinearNoiseSchedule trainers/noise_schedules.py:52-88; MeanFlowTimeSampling trainers/time_sampling.py:79-135;
-train_step trainers/training_steps.py:15-61.
+ref: LossStrategy trainers/loss_strategies.py:27-47; FlowMatchingLoss :50-112; MeanFlowLoss :115-201;
+ImprovedMeanFlowLoss :204-280; LinearNoiseSchedule / UniformNoiseSchedule trainers/noise_schedules.py:52-115;
+UniformTimeSampling / LogitNormalTimeSampling / MeanFlowTimeSampling trainers/time_sampling.py:32-135;
+create_loss_strategy trainers/train.py:52-153; train_step trainers/training_steps.py:15-61.
 """
 from __future__ import annotations
 
@@ -29,7 +30,34 @@ class LinearNoiseSchedule:
         return self.noise_max * x1 - x0
 
 
-class MeanFlowTimeSampling:
+class UniformNoiseSchedule(LinearNoiseSchedule):
+    """(1-t) x0 + t x1, target x1 - x0 (noise_schedules.py:91-115) == LinearNoiseSchedule(0, 1)."""
+
+    def __init__(self):
+        super().__init__(0.0, 1.0)
+
+
+class UniformTimeSampling:
+    """t ~ U[0, 1) (time_sampling.py:32-42)."""
+
+    def sample_time(self, key, batch_size: int, dtype=torch.float32, device="cuda"):
+        gen = torch.Generator(device="cpu").manual_seed(int(key))
+        return torch.rand(batch_size, 1, generator=gen, dtype=torch.float32).to(device=device, dtype=dtype)
+
+
+class LogitNormalTimeSampling:
+    """t = sigmoid(mean + std N(0,1)) (time_sampling.py:45-70, utils.py:32-33)."""
+
+    def __init__(self, mean: float = -0.4, std: float = 1.0):
+        self.mean, self.std = mean, std
+
+    def sample_time(self, key, batch_size: int, dtype=torch.float32, device="cuda"):
+        gen = torch.Generator(device="cpu").manual_seed(int(key))
+        n = torch.randn(batch_size, 1, generator=gen, dtype=torch.float32)
+        return torch.sigmoid(n * self.std + self.mean).to(device=device, dtype=dtype)
+
+
+class MeanFlowTimeSampling(LogitNormalTimeSampling):
     def __init__(self, mean: float = -0.4, std: float = 1.0, data_proportion: float = 0.5):
         self.mean, self.std, self.data_proportion = mean, std, data_proportion
 
@@ -51,26 +79,32 @@ class LossStrategy(ABC):
         """-> (loss, grads)"""
 
 
-class ImprovedMeanFlowLoss(LossStrategy):
-    """v_pred = u + (t - r) * stop_gradient(du/dt), weighted-L2 against noise_max*e - x.
+class _FusedLossStrategy(LossStrategy):
+    """Shared host side of the three strategies: all of them run ``mfac_imf_loss_grad`` with a different ``method``.
 
     ``key`` is an integer seed (the reference passes a jax PRNGKey).  Like the reference
      the same key gives the same (e, t, r); pass ``step=`` to advance the counter
     stream, or ``noise=``, ``t=``, ``r=`` to pin the draws explicitly (parity tests).
     """
 
-    def __init__(self, noise_schedule: LinearNoiseSchedule | None = None,
-                 time_sampling: MeanFlowTimeSampling | None = None, use_weighted_loss: bool = True):
-        self.noise_schedule = noise_schedule or LinearNoiseSchedule()
-        self.time_sampling = time_sampling or MeanFlowTimeSampling()
-        self.use_weighted_loss = use_weighted_loss
-        self.last_aux = None
+    method = _lib.LOSS_IMPROVED_MEAN_FLOW
+    gamma = 0.5
+    c = 1e-3
+    use_weighted_loss = True
+    last_aux = None
+
+    def _schedule(self):
+        return self.noise_schedule.noise_min, self.noise_schedule.noise_max
 
     def _config(self, seed: int, step: int, row_offset: int, step_dev=None) -> _lib.ImfConfig:
-        ns, ts = self.noise_schedule, self.time_sampling
-        return _lib.ImfConfig(ns.noise_min, ns.noise_max, ts.mean, ts.std, ts.data_proportion, 1e-3,
+        ts = self.time_sampling
+        nmin, nmax = self._schedule()
+        uniform = isinstance(ts, UniformTimeSampling)
+        return _lib.ImfConfig(nmin, nmax, getattr(ts, "mean", -0.4), getattr(ts, "std", 1.0),
+                              getattr(ts, "data_proportion", 0.5), self.c,
                               1 if self.use_weighted_loss else 0, int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
-                              None if step_dev is None else step_dev.data_ptr())
+                              None if step_dev is None else step_dev.data_ptr(), self.method, self.gamma,
+                              1 if uniform else 0)
 
     def compute_loss(self, state: TrainState, key, x, *, noise=None, t=None, r=None, step: int | None = None,
                      row_offset: int = 0, return_aux: bool = False, step_tensor=None, grad_ready=None):
@@ -104,7 +138,7 @@ class ImprovedMeanFlowLoss(LossStrategy):
             aux = _lib.ImfAux(*([None] * 7), cb_keep, None)
         if return_aux:
             D = model.noise_dimension
-            aux_t = {k: torch.empty((B, D), dtype=torch.float32, device=dev) for k in ("v", "u", "dudt", "e")}
+            aux_t = {k: torch.zeros((B, D), dtype=torch.float32, device=dev) for k in ("v", "u", "dudt", "e")}
             aux_t.update({k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("per_example", "t", "r")})
             aux = _lib.ImfAux(*[aux_t[k].data_ptr() for k in ("v", "u", "dudt", "per_example", "e", "t", "r")])
         cfg = self._config(int(key) if not isinstance(key, torch.Tensor) else int(key.sum()), state.step if step is None else step,
@@ -125,10 +159,101 @@ class ImprovedMeanFlowLoss(LossStrategy):
         return loss, gtree
 
 
+class ImprovedMeanFlowLoss(_FusedLossStrategy):
+    """v_pred = u + (t - r) * stop_gradient(du/dt) with the network's own v = f(z, [t, 0]) as the JVP tangent,
+    weighted-L2 against noise_max*e - x (loss_strategies.py:204-280)."""
+
+    method = _lib.LOSS_IMPROVED_MEAN_FLOW
+
+    def __init__(self, noise_schedule: LinearNoiseSchedule | None = None,
+                 time_sampling: MeanFlowTimeSampling | None = None, use_weighted_loss: bool = True):
+        self.noise_schedule = noise_schedule or LinearNoiseSchedule()
+        self.time_sampling = time_sampling or MeanFlowTimeSampling()
+        self.use_weighted_loss = use_weighted_loss
+        self.last_aux = None
+
+
+class MeanFlowLoss(_FusedLossStrategy):
+    """u against e - x - clip(t - r) * stop_gradient(du/dt), JVP along (e - x, 1, 0), adaptive weight
+    1 / (mean_D err^2 + c)^(1 - gamma) (loss_strategies.py:115-201).  Like the reference it interpolates with
+    z = (1 - t) x + t e and target e - x whatever ``noise_schedule`` says (:161-166)."""
+
+    method = _lib.LOSS_MEAN_FLOW
+
+    def __init__(self, noise_schedule: LinearNoiseSchedule | None = None,
+                 time_sampling: MeanFlowTimeSampling | None = None, gamma: float = 0.5, c: float = 1e-3):
+        self.noise_schedule = noise_schedule or LinearNoiseSchedule()
+        self.time_sampling = time_sampling or MeanFlowTimeSampling()
+        self.gamma, self.c = gamma, c
+        self.last_aux = None
+
+    def _schedule(self):
+        return 0.0, 1.0
+
+
+class FlowMatchingLoss(_FusedLossStrategy):
+    """Single time t, h = 0, no JVP: pred = f(z_t, [t, 0], encode(x)) against the schedule's target with
+    weighted_l2_loss or plain MSE (loss_strategies.py:50-112).  ``r`` is ignored."""
+
+    method = _lib.LOSS_FLOW_MATCHING
+
+    def __init__(self, noise_schedule: LinearNoiseSchedule | None = None, time_sampling=None,
+                 use_weighted_loss: bool = True):
+        self.noise_schedule = noise_schedule or LinearNoiseSchedule()
+        self.time_sampling = time_sampling or LogitNormalTimeSampling()
+        self.use_weighted_loss = use_weighted_loss
+        self.last_aux = None
+
+    def compute_loss(self, state, key, x, *, t=None, r=None, **kw):
+        return super().compute_loss(state, key, x, t=t, r=t if r is None else r, **kw)
+
+
+def create_loss_strategy(config) -> LossStrategy:
+    """Loss strategy from a ``TrainFlowConfig``-like object (trainers/train.py:52-153): same field names, defaults,
+    fall-backs and error messages."""
+    get = lambda k: getattr(config, k, None)  # noqa: E731
+    name = get("loss_strategy")
+    if name is None:
+        name = "improved_mean_flow" if get("use_improved_mean_flow") else "flow_matching"
+    ns_name = get("noise_schedule") or "linear"
+    if ns_name == "linear":
+        noise_schedule = LinearNoiseSchedule(get("noise_min") if get("noise_min") is not None else 0.001,
+                                             get("noise_max") if get("noise_max") is not None else 0.999)
+    elif ns_name == "uniform":
+        noise_schedule = UniformNoiseSchedule()
+    else:
+        raise ValueError(f"Unknown noise_schedule: {ns_name}. Must be one of: 'linear', 'uniform'")
+    mean = get("time_sampling_mean") if get("time_sampling_mean") is not None else -0.4
+    std = get("time_sampling_std") if get("time_sampling_std") is not None else 1.0
+    ts_name = get("time_sampling") or "logit_normal"
+    if ts_name == "uniform":
+        time_sampling = UniformTimeSampling()
+    elif ts_name == "logit_normal":
+        time_sampling = LogitNormalTimeSampling(mean=mean, std=std)
+    elif ts_name == "mean_flow":
+        dp = get("time_sampling_data_proportion")
+        time_sampling = MeanFlowTimeSampling(mean=mean, std=std, data_proportion=dp if dp is not None else 0.5)
+    else:
+        raise ValueError(f"Unknown time_sampling: {ts_name}. Must be one of: 'uniform', 'logit_normal', 'mean_flow'")
+    weighted = get("use_weighted_loss") if get("use_weighted_loss") is not None else True
+    if name == "flow_matching":
+        return FlowMatchingLoss(noise_schedule=noise_schedule, time_sampling=time_sampling, use_weighted_loss=weighted)
+    if name in ("mean_flow", "improved_mean_flow"):
+        if not isinstance(time_sampling, MeanFlowTimeSampling):
+            time_sampling = MeanFlowTimeSampling(mean=get("time_sampling_mean") or -0.4, std=get("time_sampling_std") or 1.0,
+                                                 data_proportion=get("time_sampling_data_proportion") or 0.5)
+        if name == "mean_flow":
+            return MeanFlowLoss(noise_schedule=noise_schedule, time_sampling=time_sampling,
+                                gamma=get("gamma") if get("gamma") is not None else 0.5,
+                                c=get("c") if get("c") is not None else 1e-3)
+        return ImprovedMeanFlowLoss(noise_schedule=noise_schedule, time_sampling=time_sampling, use_weighted_loss=weighted)
+    raise ValueError(f"Unknown loss_strategy: {name}. Must be one of: 'flow_matching', 'mean_flow', 'improved_mean_flow'")
+
+
 def train_step(state: TrainState, key, x, loss_strategy: LossStrategy | None = None, **kw):
     """(state, loss, key) -- trainers/training_steps.py:37-61.  The key is returned unchanged, as in the reference."""
     if loss_strategy is None:
-        raise ValueError("only ImprovedMeanFlowLoss is implemented on this path; pass loss_strategy=")
+        loss_strategy = FlowMatchingLoss()   # the reference's default (training_steps.py:58-59)
     loss, grads = loss_strategy.compute_loss(state, key, x, **kw)
     state = state.apply_gradients(grads=grads)
     return state, loss, key

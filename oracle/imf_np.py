@@ -246,26 +246,61 @@ def weighted_l2(delta, p=1.0, c=1e-3):
     return (w * s).mean(), s, w
 
 
-def imf_forward(p, x, e, t, r):
-    """Steps 1-4 of loss_strategies.py:227-275 for given (e, t, r).  Returns dict of tensors."""
-    z = interpolate(x, e, t)
-    tgt = target_of(x, e)
-    lat = encode(p, x)
-    zero = np.zeros_like(t)
-    v = forward(p, z, np.concatenate([t, zero], -1), lat)
-    cache = []
+def imf_forward(p, x, e, t, r, method="improved_mean_flow", gamma=0.5, c=1e-3, use_weighted_loss=True):
+    """Forward part of the three loss strategies for given (e, t, r).  Returns dict of tensors.
+
+    improved_mean_flow  loss_strategies.py:227-275  z, target from LinearNoiseSchedule(0.001, 0.999); tangent seed = the
+                        network's own v = f(z, [t, 0]); weighted_l2_loss (p = 1, sum over D)
+    mean_flow           loss_strategies.py:144-199  z = (1-t) x + t e, target = e - x; tangent seed = target (no v pass);
+                        (t - r) clipped to [0, 1]; adaptive weight 1 / (mean_D delta^2 + c)^(1 - gamma)
+    flow_matching       loss_strategies.py:74-111   single time t (h = 0), no JVP; weighted_l2_loss or plain MSE
+    """
+    dt = x.dtype
     one = np.ones_like(t[:, 0])
-    # d/ds of th = [t, t - r] along (tdot=1, rdot=0) is [1, 1]
-    u, dudt = forward(p, z, np.concatenate([t, t - r], -1), lat, xdot=v, tdot=one, hdot=one, cache=cache)
-    v_pred = u + (t - r) * dudt
+    zero = np.zeros_like(t)
+    lat = encode(p, x)
+    cache = []
+    v = None
+    if method == "improved_mean_flow":
+        z, tgt = interpolate(x, e, t), target_of(x, e)
+        v = forward(p, z, np.concatenate([t, zero], -1), lat)
+        # d/ds of th = [t, t - r] along (tdot=1, rdot=0) is [1, 1]
+        u, dudt = forward(p, z, np.concatenate([t, t - r], -1), lat, xdot=v, tdot=one, hdot=one, cache=cache)
+        tmr = t - r
+    elif method == "mean_flow":
+        z, tgt = (1.0 - t) * x + t * e, e - x
+        u, dudt = forward(p, z, np.concatenate([t, t - r], -1), lat, xdot=tgt, tdot=one, hdot=one, cache=cache)
+        tmr = np.clip(t - r, 0.0, 1.0)
+    elif method == "flow_matching":
+        z, tgt = interpolate(x, e, t), target_of(x, e)
+        u, dudt = forward(p, z, np.concatenate([t, zero], -1), lat, xdot=np.zeros_like(z), tdot=0 * one, hdot=0 * one, cache=cache)
+        tmr = zero
+    else:
+        raise ValueError(method)
+    v_pred = u + tmr * dudt
     delta = v_pred - tgt
-    loss, s, w = weighted_l2(delta)
+    s = (delta * delta).sum(-1)
+    D = x.shape[1]
+    if method == "mean_flow":
+        dsq = s / dt.type(D)
+        w = 1.0 / (dsq + dt.type(c)) ** dt.type(1.0 - gamma)
+        loss = (w * dsq).mean()
+        gscale = w / dt.type(D)                    # d loss / d delta = 2 gscale delta / B
+    elif use_weighted_loss:
+        w = 1.0 / (s + dt.type(c))
+        loss = (w * s).mean()
+        gscale = w
+    else:
+        w = np.ones_like(s)
+        loss = (delta * delta).mean()
+        gscale = w / dt.type(D)
     return dict(z=z, target=tgt, latents=lat, v=v, u=u, dudt=dudt, v_pred=v_pred, delta=delta,
-                loss=loss, per_example=s, weights=w, cache=cache)
+                loss=loss, per_example=s, weights=w, gscale=gscale, cache=cache)
 
 
-def imf_loss_and_grads(p, x, e, t, r):
-    """(loss, grads, aux): reverse-mode recurrences of SURVEY.md row L5.
+def imf_loss_and_grads(p, x, e, t, r, method="improved_mean_flow", gamma=0.5, c=1e-3, use_weighted_loss=True):
+    """(loss, grads, aux): reverse-mode recurrences of SURVEY.md row L5 (all three loss strategies: the gradient always
+    flows through the primal network output and the encoder only).
 
     Gradient flows through the primal ``u`` and through ``encode`` only: ``v`` enters
     as a JVP tangent (jax.jvp tangents carry no cotangent back to params unless the
@@ -273,12 +308,12 @@ def imf_loss_and_grads(p, x, e, t, r):
     (t-r)*dudt is stop-gradiented, loss_strategies.py:270) and ``dudt`` is stop-gradiented.
     """
     D, L, C, nb = dims_of(p)
-    aux = imf_forward(p, x, e, t, r)
+    aux = imf_forward(p, x, e, t, r, method=method, gamma=gamma, c=c, use_weighted_loss=use_weighted_loss)
     dt = x.dtype
     B = x.shape[0]
     I = L + D
     grads = {}
-    g_x = (2.0 * aux["weights"][:, None] * aux["delta"] / dt.type(B)).astype(dt)
+    g_x = (2.0 * aux["gscale"][:, None] * aux["delta"] / dt.type(B)).astype(dt)
     g_lat = np.zeros((B, L), dtype=dt)
     for k in reversed(range(nb)):
         pre = f"blocks_{k}"

@@ -92,6 +92,42 @@ def imf_loss(p, x, e, t, r, noise_min=0.001, noise_max=0.999, c=1e-3, return_aux
     return loss
 
 
+def strategy_loss(p, x, e, t, r, method="improved_mean_flow", gamma=0.5, c=1e-3, use_weighted_loss=True):
+    """The three loss strategies of trainers/loss_strategies.py written with autograd + torch.func.jvp (cross-check of the
+    NumPy recurrences): FlowMatchingLoss :74-111, MeanFlowLoss :144-199, ImprovedMeanFlowLoss :227-277."""
+    if method == "improved_mean_flow":
+        return imf_loss(p, x, e, t, r, c=c)
+    lat = encode(p, x)
+    if method == "flow_matching":
+        z = (1.0 - t) * x + (0.001 + 0.999 * t) * e
+        target = 0.999 * e - x
+        pred = forward(p, z, torch.cat([t, torch.zeros_like(t)], dim=-1), lat)
+        delta = pred - target
+        if use_weighted_loss:
+            s = (delta * delta).sum(-1)
+            return ((1.0 / (s + c)).detach() * s).mean()
+        return (delta * delta).mean()
+    assert method == "mean_flow"
+    z = (1.0 - t) * x + t * e
+    target = e - x
+
+    def u_fn(z_, t_, r_):
+        return forward(p, z_, torch.cat([t_, t_ - r_], dim=-1), lat)
+
+    u, dudt = torch.func.jvp(u_fn, (z, t, r), (target, torch.ones_like(t), torch.zeros_like(r)))
+    err = u - (target - torch.clamp(t - r, 0.0, 1.0) * dudt.detach())
+    dsq = (err * err).mean(-1)
+    w = (1.0 / (dsq + c) ** (1.0 - gamma)).detach()
+    return (w * dsq).mean()
+
+
+def strategy_loss_and_grads(p, x, e, t, r, **kw):
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    loss = strategy_loss(p, x, e, t, r, **kw)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in p.items()}
+
+
 def imf_loss_and_grads(p, x, e, t, r):
     p = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
     loss, aux = imf_loss(p, x, e, t, r, return_aux=True)

@@ -124,3 +124,44 @@ def test_tokenization_factory_from_reference_config():
     Cfg.tokenization_strategy = "wavelet"
     with pytest.raises(ValueError):
         m.create_tokenization_strategy(Cfg)
+
+
+def test_imf_config_struct_matches_header():
+    """The ctypes mirror of MfacImfConfig has the header's fields in the header's order (and C's layout)."""
+    text = (ROOT / "include" / "mfac.h").read_text()
+    body = re.search(r"typedef struct MfacImfConfig \{(.*?)\} MfacImfConfig;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [re.search(r"(\w+)\s*$", v.strip()).group(1) for d in body.split(";") if d.strip() for v in d.split(",")]
+    assert names == [f[0] for f in _lib.ImfConfig._fields_]
+    assert C.sizeof(_lib.ImfConfig) == 6 * 4 + 4 + 4 + 3 * 8 + 8 + 4 + 4 + 4 + 4  # floats, flag, pad, u64s, ptr, 3 new, tail pad
+    assert (_lib.LOSS_IMPROVED_MEAN_FLOW, _lib.LOSS_MEAN_FLOW, _lib.LOSS_FLOW_MATCHING) == (0, 1, 2)
+    for name, val in (("MFAC_LOSS_IMPROVED_MEAN_FLOW", 0), ("MFAC_LOSS_MEAN_FLOW", 1), ("MFAC_LOSS_FLOW_MATCHING", 2)):
+        assert re.search(rf"{name} = {val}\b", text)
+
+
+def test_create_loss_strategy_follows_the_reference_factory():
+    """trainers/train.py:52-153: names, defaults, fall-backs and errors."""
+    cfg = lambda **kw: type("Cfg", (), kw)()  # noqa: E731
+    s = m.create_loss_strategy(cfg(use_improved_mean_flow=True))
+    assert isinstance(s, m.ImprovedMeanFlowLoss) and isinstance(s.time_sampling, m.MeanFlowTimeSampling)
+    assert (s.noise_schedule.noise_min, s.noise_schedule.noise_max) == (0.001, 0.999)
+    s = m.create_loss_strategy(cfg(use_improved_mean_flow=False))
+    assert isinstance(s, m.FlowMatchingLoss) and type(s.time_sampling) is m.LogitNormalTimeSampling
+    s = m.create_loss_strategy(cfg(loss_strategy="flow_matching", noise_schedule="uniform", time_sampling="uniform",
+                                   use_weighted_loss=False))
+    assert isinstance(s.noise_schedule, m.UniformNoiseSchedule) and isinstance(s.time_sampling, m.UniformTimeSampling)
+    c = s._config(1, 2, 3)
+    assert (c.noise_min, c.noise_max, c.uniform_time, c.use_weighted_loss, c.method) == (0.0, 1.0, 1, 0, _lib.LOSS_FLOW_MATCHING)
+    s = m.create_loss_strategy(cfg(loss_strategy="mean_flow", gamma=0.25, c=1e-2, time_sampling_data_proportion=0.75,
+                                   time_sampling="mean_flow"))
+    assert isinstance(s, m.MeanFlowLoss) and (s.gamma, s.c, s.time_sampling.data_proportion) == (0.25, 1e-2, 0.75)
+    c = s._config(1, 2, 3)
+    assert (c.noise_min, c.noise_max, c.method) == (0.0, 1.0, _lib.LOSS_MEAN_FLOW)   # loss_strategies.py:161-166
+    assert abs(c.gamma - 0.25) < 1e-7 and abs(c.loss_c - 1e-2) < 1e-9
+    for bad in (dict(loss_strategy="rectified"), dict(noise_schedule="cosine"), dict(time_sampling="beta")):
+        with pytest.raises(ValueError):
+            m.create_loss_strategy(cfg(**bad))
+    t = m.LogitNormalTimeSampling().sample_time(0, 1000, device="cpu")
+    assert t.shape == (1000, 1) and 0.38 < float(t.mean()) < 0.46
+    u = m.UniformTimeSampling().sample_time(0, 1000, device="cpu")
+    assert u.shape == (1000, 1) and 0.45 < float(u.mean()) < 0.55

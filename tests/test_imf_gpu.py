@@ -300,3 +300,57 @@ def test_full_size_step_properties(cuda, B):
     delta_u = big["u"] - (0.999 * e - x)
     s_u = (delta_u[tr0] ** 2).sum(1)
     assert float((s_u - big["per_example"][tr0]).abs().max() / s_u.max()) < 1e-5
+
+
+@pytest.mark.parametrize("method,weighted", [("flow_matching", True), ("flow_matching", False), ("mean_flow", True)])
+def test_other_loss_strategies(setup, method, weighted):
+    """FlowMatchingLoss (loss_strategies.py:50-112) and MeanFlowLoss (:115-201) on the same fused kernels: intermediates,
+    loss and gradients against the fp64 oracle, bf16 operands / fp32 accumulate tolerance."""
+    m, model, tree, p_np, (D, L, C, nb, B) = setup
+    x, e, t, r = _inputs(D, B, seed=11)
+    if method == "flow_matching":
+        r = t.copy()
+    loss_ref, g_ref, aux_ref = imf_np.imf_loss_and_grads(as64(p_np), x.astype(np.float64), e.astype(np.float64),
+                                                         t.astype(np.float64), r.astype(np.float64), method=method,
+                                                         use_weighted_loss=weighted)
+    state = m.TrainState.create(apply_fn=model.apply, params=tree, tx=m.adamw(1e-4, 1e-4))
+    strat = m.MeanFlowLoss(gamma=0.5, c=1e-3) if method == "mean_flow" else m.FlowMatchingLoss(use_weighted_loss=weighted)
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kw = dict(noise=c(e), t=c(t[:, 0]), return_aux=True)
+    if method == "mean_flow":
+        kw["r"] = c(r[:, 0])
+    loss, grads, aux = strat.compute_loss(state, 0, c(x), **kw)
+    torch.cuda.synchronize()
+    assert rel_l2(aux["u"].cpu().numpy(), aux_ref["u"]) < TOL
+    if method == "mean_flow":
+        assert rel_l2(aux["dudt"].cpu().numpy(), aux_ref["dudt"]) < TOL
+    assert rel_l2(aux["per_example"].cpu().numpy(), aux_ref["per_example"]) < 2 * TOL
+    assert abs(float(loss) - loss_ref) < 2e-2 * abs(loss_ref) + 1e-4
+    g = tree_to_np(grads)
+    flat = np.concatenate([g[k].ravel() for k in g_ref])
+    flat_ref = np.concatenate([g_ref[k].ravel() for k in g_ref])
+    worst = max((rel_l2(g[k], g_ref[k]), k) for k in g_ref)
+    assert rel_l2(flat, flat_ref) < TOL, worst
+    assert worst[0] < 3 * TOL, worst
+
+
+def test_default_train_step_is_flow_matching_and_internal_rng(cuda):
+    """train_step(loss_strategy=None) is FlowMatchingLoss (training_steps.py:58-59); with the internal RNG flow matching
+    draws a single time (r == t) and UniformTimeSampling covers (0, 1) evenly."""
+    import meanflow_audio_codec_b200 as m
+    D, L, C, nb, B = 128, 64, 32, 2, 4096
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=to_device_tree(oracle_params(D, L, C, nb)), tx=m.adamw(1e-4, 1e-4))
+    x = torch.rand(B, D, device="cuda") * 2 - 1
+    state2, loss, key = m.train_step(state, 7, x)
+    assert state2.step == 1 and torch.isfinite(loss)
+    for ts, lo, hi in ((m.UniformTimeSampling(), 0.48, 0.52), (m.LogitNormalTimeSampling(-0.4, 1.0), 0.40, 0.44)):
+        strat = m.FlowMatchingLoss(time_sampling=ts)
+        _, _, aux = strat.compute_loss(state, 7, x, return_aux=True)
+        t, r = aux["t"].cpu().numpy(), aux["r"].cpu().numpy()
+        assert (t == r).all() and (t > 0).all() and (t < 1).all()
+        assert lo < t.mean() < hi, t.mean()
+    strat = m.create_loss_strategy(type("Cfg", (), dict(loss_strategy="mean_flow", gamma=0.3))())
+    assert isinstance(strat, m.MeanFlowLoss) and strat.gamma == 0.3
+    loss, _ = strat.compute_loss(state, 7, x)
+    assert torch.isfinite(loss)

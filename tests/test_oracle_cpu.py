@@ -183,3 +183,32 @@ def test_adamw_matches_torch_reference_impl():
     p1, _, _ = imf_np.adamw_step(p0, g, {q: np.zeros_like(v) for q, v in p0.items()}, {q: np.zeros_like(v) for q, v in p0.items()}, 0)
     step_size = np.abs(p1[k] - p0[k] * (1 - 1e-4 * 1e-4))
     assert np.median(step_size) == pytest.approx(1e-4, rel=1e-3)
+
+
+@pytest.mark.parametrize("method,weighted", [("flow_matching", True), ("flow_matching", False), ("mean_flow", True),
+                                             ("improved_mean_flow", True)])
+def test_loss_strategies_recurrences_match_autograd(method, weighted):
+    """The three strategies of trainers/loss_strategies.py (FlowMatchingLoss :74-111, MeanFlowLoss :144-199,
+    ImprovedMeanFlowLoss :227-277): NumPy recurrences == torch autograd + torch.func.jvp."""
+    p, x, e, t, r = _setup(seed=2)
+    if method == "flow_matching":
+        r = t.copy()
+    loss, g, _ = imf_np.imf_loss_and_grads(p, x, e, t, r, method=method, use_weighted_loss=weighted)
+    pt = {k: torch.from_numpy(v) for k, v in p.items()}
+    lt, gt = imf_torch.strategy_loss_and_grads(pt, *(torch.from_numpy(a) for a in (x, e, t, r)), method=method,
+                                               use_weighted_loss=weighted)
+    assert abs(loss - float(lt)) < 1e-12
+    for k in g:
+        np.testing.assert_allclose(g[k], gt[k].numpy(), atol=1e-12, err_msg=k)
+
+
+def test_mean_flow_clips_t_minus_r_and_weights():
+    """loss_strategies.py:178 clips (t - r) to [0, 1]; :190-191 w = 1/(mean_D err^2 + c)^(1 - gamma)."""
+    p, x, e, t, r = _setup(seed=3)
+    a = imf_np.imf_forward(p, x, e, r, t, method="mean_flow")          # t < r on purpose: clip -> 0
+    np.testing.assert_allclose(a["v_pred"], a["u"], atol=0)
+    for gamma in (0.0, 0.5, 1.0):
+        a = imf_np.imf_forward(p, x, e, t, r, method="mean_flow", gamma=gamma)
+        dsq = (a["delta"] ** 2).mean(-1)
+        np.testing.assert_allclose(a["weights"], (dsq + 1e-3) ** (gamma - 1.0), rtol=1e-12)
+        assert abs(a["loss"] - (a["weights"] * dsq).mean()) < 1e-14
