@@ -354,3 +354,33 @@ def test_default_train_step_is_flow_matching_and_internal_rng(cuda):
     assert isinstance(strat, m.MeanFlowLoss) and strat.gamma == 0.3
     loss, _ = strat.compute_loss(state, 7, x)
     assert torch.isfinite(loss)
+
+
+def test_checkpoint_resume_continues_bit_identically(cuda, tmp_path):
+    """save_checkpoint / load_checkpoint (trainers/utils.py:45-58) through the device state: a run resumed from the
+    msgpack file takes exactly the steps of the uninterrupted run (params, moments, count and RNG step restored)."""
+    import meanflow_audio_codec_b200 as m
+    from meanflow_audio_codec_b200 import checkpoint as ck
+    D, L, C, nb, B = 128, 64, 32, 2, 64
+    x = torch.rand(B, D, device="cuda") * 2 - 1
+    strat = m.ImprovedMeanFlowLoss()
+
+    def fresh(seed):
+        model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+        return m.TrainState.create(apply_fn=model.apply, params=model.init(seed)["params"], tx=m.adamw(1e-3, 1e-4))
+    state = fresh(0)
+    for _ in range(3):
+        state, _, _ = m.train_step(state, 5, x, strat)
+    ck.save_checkpoint(tmp_path / "step_00003.msgpack", state)
+    ref_losses = []
+    for _ in range(2):
+        state, loss, _ = m.train_step(state, 5, x, strat)
+        ref_losses.append(float(loss))
+    resumed = ck.load_checkpoint(tmp_path / "step_00003.msgpack", fresh(123))
+    assert resumed.step == 3 and resumed.opt_state["count"] == 3
+    got = []
+    for _ in range(2):
+        resumed, loss, _ = m.train_step(resumed, 5, x, strat)
+        got.append(float(loss))
+    assert got == ref_losses
+    assert torch.equal(resumed.model.flat_params(resumed.params).flat, state.model.flat_params(state.params).flat)
