@@ -378,7 +378,12 @@ def run_mfac(args):
             "config": workload_config(args, B, D, nf),
             "e2e": e2e, "gpu_launches": main["launches"], "clocks": main["clocks"],
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "tensor_frac_whole_step": flops_per_sample(D) * B / (main["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"],
+            # executed tensor FLOPs of a step (counted per GEMM launch) over the whole step time; the "reference_flops"
+            # figure divides the FLOPs the reference's schedule would spend (three full network evaluations +
+            # tangent + backward) -- the step shares one evaluation between u and v on the rows with r == t
+            "tensor_frac_whole_step": ((roofline["flops_per_step_measured"] if roofline else flops_per_sample(D) * B)
+                                       / (main["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"]),
+            "tensor_frac_whole_step_reference_flops": flops_per_sample(D) * B / (main["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"],
             "kernel_families": families, "sweep": sweep, "codec": codec,
             "wall_ms_per_step": main["wall_ms"] / args.steps, "loss": main["loss"],
         }

@@ -29,6 +29,7 @@ class ImfConfig(C.Structure):
         ("seed", C.c_uint64), ("step", C.c_uint64), ("row_offset", C.c_uint64),
         ("step_dev", C.c_void_p),
         ("method", C.c_int32), ("gamma", C.c_float), ("uniform_time", C.c_int32),
+        ("rows_r_equals_t", C.c_int64),
     ]
 
 

@@ -357,38 +357,86 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   if (cfg->method < MFAC_LOSS_IMPROVED_MEAN_FLOW || cfg->method > MFAC_LOSS_FLOW_MATCHING) return MFAC_ERR_UNSUPPORTED;
   const bool need_v = cfg->method == MFAC_LOSS_IMPROVED_MEAN_FLOW;   // tangent seed = the network's own velocity
   const bool tangent = cfg->method != MFAC_LOSS_FLOW_MATCHING;       // flow matching has no JVP
-  // z_t -> xs[0] (u pass) and, for improved mean flow, v (v pass, in place); mean flow seeds the tangent with e - x
-  PrepArgs pa{x, e, t, r, p.e, need_v ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
-              p.xb, p.t, p.r, p.cond_v, p.cond_u, p.dcond_u, *cfg, B};
+  // Rows [0, h) have r == t (sample_tr's rule, utils.py:41-44): there the u pass sees exactly the input and the (t, 0)
+  // conditioning of the v pass, so ONE saved primal pass serves as both.  h comes from the library's own draw, or from
+  // the caller's promise for explicit (t, r).
+  int64_t h = 0;
+  if (need_v && cfg->rows_r_equals_t >= 0)
+    h = t ? (cfg->rows_r_equals_t < B ? cfg->rows_r_equals_t : B) : (int64_t)((float)B * cfg->data_proportion);
+  if (h < 0) h = 0;
+  if (h > B) h = B;
+  const bool share = need_v && h * 4 >= B;
+  if (!share) h = 0;
+  const int Mu = (int)(B - h);   // rows whose u pass differs from their v pass
+  // z_t -> xs[0] (u pass) and, for improved mean flow without sharing, v (v pass, in place); mean flow seeds the tangent
+  // with e - x
+  PrepArgs pa{x, e, t, r, p.e, need_v && !share ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
+              p.xb, p.t, p.r, need_v ? p.cond_v : nullptr, p.cond_u, p.dcond_u, *cfg, B};
   imf_prep_kernel<<<(unsigned)B, ROW_THREADS, 0, s>>>(pa, d);
   count_launch();
   // ---- latents = encode(x)
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
-  // ---- v = f(z, [t, 0], lat)
-  if (need_v) MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
-  // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
-  // first modulation layer of all blocks, primal and tangent, in two GEMMs
-  MFAC_OK(gemm_bias_gelu(p.cond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
-  if (tangent) MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
-  for (int k = 0; k < d.nb; ++k) {
+  // one block of the saved primal pass over rows [r0, r0 + rows): activations go to the per-block buffers the tangent
+  // pass and the backward read
+  auto primal_mod = [&](int k, int64_t r0, int rows) -> int {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
     SavedBlock& sb = p.blk[k];
+    return gemm_linear_bf16(sb.gc + r0 * d.Ca, d.Ca, w + d.s_c2w, rows, d.Mp, d.Cp, bias + d.b_c2, sb.m + r0 * d.Mp, d.Mp, s);
+  };
+  auto primal_mlp = [&](int k, int64_t r0, int rows) -> int {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    const float* bias = sh.b + k * d.b_blk_stride;
+    SavedBlock& sb = p.blk[k];
+    float* x_in = p.xs + (int64_t)k * B * d.Dp + r0 * d.Dp;
+    float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp + r0 * d.Dp;
+    MFAC_OK(gemm_bias_gelu(sb.hin + r0 * d.Ip, d.Ip, w + d.s_m1w, rows, d.Ip, d.Ip, bias + d.b_m1, sb.g + r0 * d.Ip,
+                           sb.a + r0 * d.Ip, d.Ip, s));
+    return gemm_fwd(sb.g + r0 * d.Ip, d.Ip, w + d.s_m2w, rows, d.Dp, d.Ip,
+                    EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s);
+  };
+  // ---- v = f(z, [t, 0], lat)
+  if (share) {
+    // saved primal pass over ALL rows with the (t, 0) conditioning: v for every row, and already u (with every
+    // activation the tangent pass and the backward need) for rows [0, h)
+    MFAC_OK(gemm_bias_gelu(p.cond_v, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
+    for (int k = 0; k < d.nb; ++k) {
+      SavedBlock& sb = p.blk[k];
+      MFAC_OK(primal_mod(k, 0, M));
+      LnModArgs la{p.lat, p.xs + (int64_t)k * B * d.Dp, sb.m, sb.hin, nullptr, nullptr, nullptr, sb.mu, sb.rstd, d.Mp};
+      MFAC_OK(lnmod(false, la, d, B, s));
+      MFAC_OK(primal_mlp(k, 0, M));
+    }
+    MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.xs + (int64_t)d.nb * B * d.Dp, (size_t)B * d.Dp * 4, cudaMemcpyDeviceToDevice, s));
+  } else if (need_v) {
+    MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
+  }
+  // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
+  // first modulation layer of all blocks, primal and tangent, in two GEMMs
+  if (Mu > 0)
+    MFAC_OK(gemm_bias_gelu(p.cond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all + h * d.Ca,
+                           p.ac_all + h * d.Ca, d.Ca, s));
+  if (tangent) MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
+  for (int k = 0; k < d.nb; ++k) {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    SavedBlock& sb = p.blk[k];
     float* x_in = p.xs + (int64_t)k * B * d.Dp;
-    float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp;
     const float* xd_in = k == 0 ? p.v : p.xd;
-    // modulation, primal and tangent
-    MFAC_OK(gemm_linear_bf16(sb.gc, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, bias + d.b_c2, sb.m, d.Mp, s));
+    // modulation, primal (rows [h, B): rows [0, h) keep the shared pass's) and tangent
+    if (Mu > 0) MFAC_OK(primal_mod(k, h, Mu));
     if (tangent) MFAC_OK(gemm_linear_bf16(p.gcd + k * d.Cp, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
+    // all rows: rows [0, h) re-derive the same hin / statistics from the same inputs, and get their tangent
     LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd, d.Mp};
     MFAC_OK(lnmod(tangent, la, d, B, s));
-    MFAC_OK(gemm_bias_gelu(sb.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sb.g, sb.a, d.Ip, s));
-    if (tangent) MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
-    MFAC_OK(gemm_fwd(sb.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
-                     EpiBlockOut{bias + d.b_m2, sb.m, x_in, x_out, sb.o, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
-    if (tangent)
+    if (tangent) {
+      // the tangent GEMMs read the primal pre-activation a and block output o: primal first
+      if (Mu > 0) MFAC_OK(primal_mlp(k, h, Mu));
+      MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
       MFAC_OK(gemm_fwd(p.gd, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
                        EpiBlockOutTangent{sb.m, p.md, sb.o, xd_in, p.xd, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
+    } else {
+      MFAC_OK(primal_mlp(k, 0, M));
+    }
   }
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
   // ---- loss and its seed gradient

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
       a.xb[b * d.Dp + j] = __float2bfloat16(xv);
     }
   }
-  if (a.z) write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + b * d.Cp, nullptr);
+  if (a.cond_v) write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + b * d.Cp, nullptr);
   write_cond_row(t, t - r, d.C, d.Cp, a.cond_u + b * d.Cp, a.dcond_u + b * d.Cp);
 }
 

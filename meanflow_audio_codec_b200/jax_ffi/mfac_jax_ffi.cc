@@ -83,7 +83,7 @@ static ffi::Error ImfLossGradImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> par
                                   ffi::Buffer<ffi::F32> r, ffi::ResultBuffer<ffi::F32> loss, ffi::ResultBuffer<ffi::F32> grads,
                                   ffi::ResultBuffer<ffi::U8> ws, int32_t D, int32_t L, int32_t C, int32_t nb) {
   MfacMlpDims dims{D, L, C, nb};
-  MfacImfConfig cfg{0.001f, 0.999f, -0.4f, 1.0f, 0.5f, 1e-3f, 1, 0, 0, 0, nullptr, MFAC_LOSS_IMPROVED_MEAN_FLOW, 0.5f, 0};
+  MfacImfConfig cfg{0.001f, 0.999f, -0.4f, 1.0f, 0.5f, 1e-3f, 1, 0, 0, 0, nullptr, MFAC_LOSS_IMPROVED_MEAN_FLOW, 0.5f, 0, 0};
   const int64_t B = x.dimensions()[0];
   return status_of(mfac_imf_loss_grad(&dims, &cfg, params.typed_data(), shadow.typed_data(), x.typed_data(), e.typed_data(),
                                       t.typed_data(), r.typed_data(), loss->typed_data(), grads->typed_data(), nullptr, B,

@@ -96,7 +96,7 @@ class _FusedLossStrategy(LossStrategy):
     def _schedule(self):
         return self.noise_schedule.noise_min, self.noise_schedule.noise_max
 
-    def _config(self, seed: int, step: int, row_offset: int, step_dev=None) -> _lib.ImfConfig:
+    def _config(self, seed: int, step: int, row_offset: int, step_dev=None, rows_r_equals_t: int = 0) -> _lib.ImfConfig:
         ts = self.time_sampling
         nmin, nmax = self._schedule()
         uniform = isinstance(ts, UniformTimeSampling)
@@ -104,11 +104,14 @@ class _FusedLossStrategy(LossStrategy):
                               getattr(ts, "data_proportion", 0.5), self.c,
                               1 if self.use_weighted_loss else 0, int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
                               None if step_dev is None else step_dev.data_ptr(), self.method, self.gamma,
-                              1 if uniform else 0)
+                              1 if uniform else 0, int(rows_r_equals_t))
 
     def compute_loss(self, state: TrainState, key, x, *, noise=None, t=None, r=None, step: int | None = None,
-                     row_offset: int = 0, return_aux: bool = False, step_tensor=None, grad_ready=None):
-        """``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay).
+                     row_offset: int = 0, return_aux: bool = False, step_tensor=None, grad_ready=None,
+                     rows_r_equals_t: int = 0):
+        """``rows_r_equals_t``: with explicit ``t``/``r``, a promise that the first so many rows have r == t (the rule
+        ``sample_tr`` applies, utils.py:41-44) -- their u pass then doubles as their v pass; -1 disables that sharing for the
+        internal draws too.  ``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay).
         ``grad_ready(flat_slice)``: optional host callback, called as soon as the launches that finalise a slice of the
         flat gradient are enqueued (block by block, last block first, encoder last) -- data_parallel.py starts that
         bucket's all-reduce from it."""
@@ -142,7 +145,7 @@ class _FusedLossStrategy(LossStrategy):
             aux_t.update({k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("per_example", "t", "r")})
             aux = _lib.ImfAux(*[aux_t[k].data_ptr() for k in ("v", "u", "dudt", "per_example", "e", "t", "r")])
         cfg = self._config(int(key) if not isinstance(key, torch.Tensor) else int(key.sum()), state.step if step is None else step,
-                           row_offset, step_tensor)
+                           row_offset, step_tensor, rows_r_equals_t)
         ws = model.workspace(_lib.WS_LOSS_GRAD, B, dev)
         ptr = lambda a: None if a is None else a.data_ptr()  # noqa: E731
         with torch.cuda.device(dev):

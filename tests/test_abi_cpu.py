@@ -133,7 +133,7 @@ def test_imf_config_struct_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = [re.search(r"(\w+)\s*$", v.strip()).group(1) for d in body.split(";") if d.strip() for v in d.split(",")]
     assert names == [f[0] for f in _lib.ImfConfig._fields_]
-    assert C.sizeof(_lib.ImfConfig) == 6 * 4 + 4 + 4 + 3 * 8 + 8 + 4 + 4 + 4 + 4  # floats, flag, pad, u64s, ptr, 3 new, tail pad
+    assert C.sizeof(_lib.ImfConfig) == 6 * 4 + 4 + 4 + 3 * 8 + 8 + 4 + 4 + 4 + 4 + 8  # floats, flag, pad, u64s, ptr, 3 x 4, pad, i64
     assert (_lib.LOSS_IMPROVED_MEAN_FLOW, _lib.LOSS_MEAN_FLOW, _lib.LOSS_FLOW_MATCHING) == (0, 1, 2)
     for name, val in (("MFAC_LOSS_IMPROVED_MEAN_FLOW", 0), ("MFAC_LOSS_MEAN_FLOW", 1), ("MFAC_LOSS_FLOW_MATCHING", 2)):
         assert re.search(rf"{name} = {val}\b", text)

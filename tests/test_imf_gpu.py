@@ -384,3 +384,36 @@ def test_checkpoint_resume_continues_bit_identically(cuda, tmp_path):
         got.append(float(loss))
     assert got == ref_losses
     assert torch.equal(resumed.model.flat_params(resumed.params).flat, state.model.flat_params(state.params).flat)
+
+
+def test_shared_pass_for_rows_with_r_equal_t(setup):
+    """utils.py:41-44 gives the first int(B * data_proportion) rows r = t; on those rows f(z, [t, t - r]) is the v
+    evaluation f(z, [t, 0]), so the step runs ONE saved primal pass for them (MfacImfConfig.rows_r_equals_t).  The
+    shared schedule must give the bits of the plain one (same dot products, same order) and still match the oracle."""
+    m, model, tree, p_np, (D, L, C, nb, B) = setup
+    x, e, t, r = _inputs(D, B)
+    hrows = int(B * 0.5)
+    assert (t[:hrows] == r[:hrows]).all() and hrows * 4 >= B
+    state = m.TrainState.create(apply_fn=model.apply, params=tree, tx=m.adamw(1e-4, 1e-4))
+    strat = m.ImprovedMeanFlowLoss()
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kw = dict(noise=c(e), t=c(t[:, 0]), r=c(r[:, 0]), return_aux=True)
+    l0, g0, a0 = strat.compute_loss(state, 0, c(x), **kw)
+    l1, g1, a1 = strat.compute_loss(state, 0, c(x), rows_r_equals_t=hrows, **kw)
+    for k in ("v", "u", "dudt", "per_example"):
+        assert torch.equal(a0[k], a1[k]), k
+    assert float(l0) == float(l1)
+    f0, f1 = g0.flat.cpu().numpy(), g1.flat.cpu().numpy()
+    assert rel_l2(f1, f0) < 1e-5            # split-K partial sums are accumulated atomically: order varies run to run
+    loss_ref, g_ref, aux_ref = imf_np.imf_loss_and_grads(as64(p_np), x.astype(np.float64), e.astype(np.float64),
+                                                         t.astype(np.float64), r.astype(np.float64))
+    g = tree_to_np(g1)
+    flat = np.concatenate([g[k].ravel() for k in g_ref])
+    flat_ref = np.concatenate([g_ref[k].ravel() for k in g_ref])
+    assert rel_l2(flat, flat_ref) < TOL and abs(float(l1) - loss_ref) < 1e-4
+    # the library's own draws apply the rule themselves: sharing on (default) and off (-1) agree bit for bit
+    _, _, b0 = strat.compute_loss(state, 9, c(x), return_aux=True, rows_r_equals_t=-1)
+    _, _, b1 = strat.compute_loss(state, 9, c(x), return_aux=True)
+    assert torch.equal(b0["t"][:hrows], b0["r"][:hrows])
+    for k in ("e", "t", "r", "v", "u", "dudt", "per_example"):
+        assert torch.equal(b0[k], b1[k]), k
