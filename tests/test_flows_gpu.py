@@ -89,3 +89,52 @@ def test_factory_dispatch(m):
     Cfg.architecture = "transformer"
     with pytest.raises(ValueError):
         m.create_flow_model(Cfg)
+
+
+@pytest.mark.parametrize("arch", ["mlp_mixer", "convnet"])
+def test_samplers_run_on_the_other_architectures(m, arch):
+    """sample() (evaluators/sampling.py:5-95: Heun, h = 0, optional CFG) and the 1-/2-NFE mean-flow rule around the
+    mixer / ConvNeXt forward kernels, against the same loops written over the NumPy oracle's forward."""
+    from oracle import flows_np
+    D, C, nb, B = 64, 32, 2, 5
+    if arch == "mlp_mixer":
+        model = m.ConditionalMLPMixerFlow(D, C, nb, latent_dimension=8, token_mix_dim=64, channel_mix_dim=64, num_channels=16,
+                                          num_latent_tokens=4)
+        fwd = lambda p, x, t, lat: flows_np.mixer_forward(p, x, t, lat, num_blocks=nb, num_channels=16, condition_dimension=C)  # noqa: E731
+    else:
+        model = m.ConditionalConvFlow(D, C, nb, latent_dimension=8, num_latent_tokens=4)
+        fwd = lambda p, x, t, lat: flows_np.conv_forward(p, x, t, lat, num_blocks=nb, condition_dimension=C)  # noqa: E731
+    params = model.init(3)["params"]
+    gen = torch.Generator().manual_seed(5)
+    perturb(params, gen)
+    noise = torch.randn(B, D, generator=gen)
+    lat = torch.randn(B, 4, 8, generator=gen)
+    p64, e64, l64 = tree_np(params), noise.numpy().astype(np.float64), lat.numpy().astype(np.float64)
+
+    def heun(n, gs):
+        x, dt = e64.copy(), 1.0 / n
+
+        def f(xx, tt):
+            tp = np.stack([np.full(B, tt), np.zeros(B)], -1)
+            k = fwd(p64, xx, tp, l64)
+            return k if gs == 1.0 else gs * k + (1.0 - gs) * fwd(p64, xx, tp, None)
+        for tt in np.linspace(1.0, 0.0, n):
+            k1 = f(x, tt)
+            k2 = f(x - dt * k1, tt - dt)
+            x = x - dt / 2.0 * (k1 + k2)
+        return x
+    for n, gs in ((1, 1.0), (3, 1.0), (2, 1.5)):
+        got = m.sample(model.apply, D, params, 0, latents=lat.cuda(), n_steps=n, guidance_scale=gs, noise=noise.cuda())
+        assert rel(got.cpu().numpy().astype(np.float64), heun(n, gs)) < 1e-2, (n, gs)
+    for nfe in (1, 2):
+        x = e64.copy()
+        for i in range(nfe):
+            t, r = 1.0 - i / nfe, 1.0 - (i + 1) / nfe
+            x = x - (t - r) * fwd(p64, x, np.stack([np.full(B, t), np.full(B, t - r)], -1), l64)
+        got = m.sample_mean_flow(model.apply, D, params, 0, lat.cuda(), nfe=nfe, noise=noise.cuda())
+        assert rel(got.cpu().numpy().astype(np.float64), x) < 1e-2, nfe
+    a = m.sample(model.apply, D, params, 11, latents=lat.cuda(), n_steps=1)     # drawn noise: same key, same sample
+    b = m.sample(model.apply, D, params, 11, latents=lat.cuda(), n_steps=1)
+    assert a.shape == (B, D) and torch.equal(a, b)
+    with pytest.raises(ValueError):
+        m.sample(model.apply, D, params, 0, latents=None)

@@ -145,3 +145,23 @@ def test_full_size_clips_properties(m):
 def test_empty_batch(m):
     X = m.mdct(torch.zeros(0, 1000, device="cuda"), 512, 256)
     assert tuple(X.shape) == (0, 2, 512)
+
+
+def test_spectral_distance_matches_the_reference_loop(cuda):
+    """evaluators/audio_metrics.py:141-171: mean over clips of sqrt(mean((MDCT(ref) - MDCT(deg))^2))."""
+    from meanflow_audio_codec_b200.audio_metrics import spectral_distance
+    rng = np.random.default_rng(0)
+    ref = (0.1 * rng.standard_normal((5, 4000))).astype(np.float32)
+    deg = ref + (0.01 * rng.standard_normal(ref.shape)).astype(np.float32)
+    want = np.mean([np.sqrt(np.mean((mdct_np.mdct(ref[i:i + 1].astype(np.float64), 512, 256)
+                                     - mdct_np.mdct(deg[i:i + 1].astype(np.float64), 512, 256)) ** 2)) for i in range(5)])
+    got = spectral_distance(ref, deg)
+    assert abs(got - want) < 1e-5 * want
+    one = spectral_distance(torch.from_numpy(ref[0]).cuda(), torch.from_numpy(deg[0]).cuda(), window_size=256)
+    w1 = np.sqrt(np.mean((mdct_np.mdct(ref[:1].astype(np.float64), 256, 128) - mdct_np.mdct(deg[:1].astype(np.float64), 256, 128)) ** 2))
+    assert abs(one - w1) < 1e-5 * w1
+    assert spectral_distance(ref, ref) == 0.0
+    with pytest.raises(ValueError):
+        spectral_distance(ref, deg[:, :100])
+    with pytest.raises(ValueError):
+        spectral_distance(ref, deg, domain="stft")
