@@ -78,10 +78,11 @@ int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream
     configured = true;
   }
   const int nv = vec_rows(d);
-  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8);
+  // the tangent variant keeps a whole row's operands in flight (~250 registers): 4-row CTAs so that two fit an SM
+  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8), tgrid = (unsigned)ceil_div<int64_t>(B, 4);
 #define MFAC_LNMOD_CASE(NVV)                                                              \
   case NVV:                                                                               \
-    if (tangent) lnmod_vec_kernel<NVV, true><<<vgrid, 256, 0, s>>>(a, d, B);              \
+    if (tangent) lnmod_vec_kernel<NVV, true><<<tgrid, 128, 0, s>>>(a, d, B);              \
     else lnmod_vec_kernel<NVV, false><<<vgrid, 256, 0, s>>>(a, d, B);                     \
     break;
   switch (nv) {
@@ -97,8 +98,8 @@ int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream
 }
 
 int ln_bwd(const LnBwdArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
-  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8);
-#define MFAC_LNBWD_CASE(NVV) case NVV: ln_bwd_vec_kernel<NVV><<<vgrid, 256, 0, s>>>(a, d, B); break;
+  const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 4);   // ~200 registers per thread: 4-row CTAs, two per SM
+#define MFAC_LNBWD_CASE(NVV) case NVV: ln_bwd_vec_kernel<NVV><<<vgrid, 128, 0, s>>>(a, d, B); break;
   switch (vec_rows(d)) {
     MFAC_LNBWD_CASE(1) MFAC_LNBWD_CASE(2) MFAC_LNBWD_CASE(3) MFAC_LNBWD_CASE(4)
     MFAC_LNBWD_CASE(5) MFAC_LNBWD_CASE(6) MFAC_LNBWD_CASE(7) MFAC_LNBWD_CASE(8)

@@ -419,6 +419,11 @@ __device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) 
   const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+__device__ __forceinline__ uint4 ld8_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void cvt8_bf16(const uint4 u, float (&v)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
 __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
@@ -428,7 +433,7 @@ __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) 
 template <int NV, bool TANGENT>
 __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   float c[NV][8], cd[TANGENT ? NV : 1][8];
   float sum = 0.f, sq = 0.f, sumd = 0.f;
@@ -456,6 +461,21 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
       if (TANGENT) sumd += cd[i][q];
     }
   }
+  // The stores below may alias the loads as far as the compiler can tell, so it would keep every modulation load behind
+  // the previous chunk's store (one exposed memory latency per chunk).  The tangent variant (half the occupancy of the
+  // primal one) therefore requests all of its modulation vectors here, before the reductions, and keeps them packed.
+  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
+  uint4 r_s1[TANGENT ? NV : 1], r_sh[TANGENT ? NV : 1], r_s1d[TANGENT ? NV : 1], r_shd[TANGENT ? NV : 1];
+  if (TANGENT) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = 8 * (lane + 32 * i);
+      r_s1[i] = ld8_raw(mrow + col);
+      r_sh[i] = ld8_raw(mrow + d.Ip + col);
+      r_s1d[i] = ld8_raw(a.md + b * d.Mp + col);
+      r_shd[i] = ld8_raw(a.md + b * d.Mp + d.Ip + col);
+    }
+  }
   const float inv_i = 1.0f / (float)d.I;
   const float mu = warp_sum(sum) * inv_i;
   const float rstd = rsqrtf(fmaxf(0.f, warp_sum(sq) * inv_i - mu * mu) + LN_EPS);
@@ -470,13 +490,17 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
     mean_ncd = warp_sum(acc) * inv_i;
   }
   if (lane == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
-  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = 8 * (lane + 32 * i);
     float s1[8], sh[8], h[8], n[8];
-    ld8_bf16(mrow + col, s1);
-    ld8_bf16(mrow + d.Ip + col, sh);
+    if (TANGENT) {
+      cvt8_bf16(r_s1[i], s1);
+      cvt8_bf16(r_sh[i], sh);
+    } else {
+      ld8_bf16(mrow + col, s1);
+      ld8_bf16(mrow + d.Ip + col, sh);
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       n[q] = (c[i][q] - mu) * rstd;
@@ -485,8 +509,8 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
     st8_bf16(a.hin + b * d.Ip + col, h);
     if (TANGENT) {
       float s1d[8], shd[8];
-      ld8_bf16(a.md + b * d.Mp + col, s1d);
-      ld8_bf16(a.md + b * d.Mp + d.Ip + col, shd);
+      cvt8_bf16(r_s1d[i], s1d);
+      cvt8_bf16(r_shd[i], shd);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float nd = (cd[i][q] - mean_cd - n[q] * mean_ncd) * rstd;
@@ -500,22 +524,37 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, int64_t B) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
+  // every load of the row is requested before the first store (the stores alias the loads as far as the compiler knows,
+  // which would otherwise serialise one memory latency per chunk)
+  float n[NV][8], acc[NV][8];
+  uint4 r_gh[NV], r_s1[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = 8 * (lane + 32 * i);
+    if (col < d.Lp) {
+      ld8_f32(a.lat + b * d.Lp + col, n[i]);
+      ld8_f32(a.g_lat + b * d.Lp + col, acc[i]);
+    } else {
+      ld8_f32(a.x + b * d.Dp + (col - d.Lp), n[i]);
+      ld8_f32(a.g_x + b * d.Dp + (col - d.Lp), acc[i]);
+    }
+    r_gh[i] = ld8_raw(a.g_m + b * d.Mp + d.Ip + col);
+    r_s1[i] = ld8_raw(a.m + b * d.Mp + col);
+  }
   const float mu = a.mu[b], rstd = a.rstd[b];
-  float n[NV][8], gn[NV][8];
+  float gn[NV][8];
   float s1sum = 0.f, s2sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = 8 * (lane + 32 * i);
-    float c[8], gh[8], s1[8], gs1[8];
-    if (col < d.Lp) ld8_f32(a.lat + b * d.Lp + col, c);
-    else ld8_f32(a.x + b * d.Dp + (col - d.Lp), c);
-    ld8_bf16(a.g_m + b * d.Mp + d.Ip + col, gh);
-    ld8_bf16(a.m + b * d.Mp + col, s1);
+    float gh[8], s1[8], gs1[8];
+    cvt8_bf16(r_gh[i], gh);
+    cvt8_bf16(r_s1[i], s1);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      n[i][q] = (c[q] - mu) * rstd;
+      n[i][q] = (n[i][q] - mu) * rstd;
       gn[i][q] = gh[q] * (1.0f + s1[q]);
       gs1[q] = gh[q] * n[i][q];
       s1sum += gn[i][q];
@@ -529,11 +568,9 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
   for (int i = 0; i < NV; ++i) {
     const int col = 8 * (lane + 32 * i);
     float* dst = col < d.Lp ? a.g_lat + b * d.Lp + col : a.g_x + b * d.Dp + (col - d.Lp);
-    float acc[8];
-    ld8_f32(dst, acc);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] += (gn[i][q] - m1 - n[i][q] * m2) * rstd;
-    st8_f32(dst, acc);
+    for (int q = 0; q < 8; ++q) acc[i][q] += (gn[i][q] - m1 - n[i][q] * m2) * rstd;
+    st8_f32(dst, acc[i]);
   }
 }
 
