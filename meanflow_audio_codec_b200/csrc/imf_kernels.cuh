@@ -431,7 +431,7 @@ __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) 
 }
 
 template <int NV, bool TANGENT>
-__global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
+__global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -472,8 +472,6 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
       const int col = 8 * (lane + 32 * i);
       r_s1[i] = ld8_raw(mrow + col);
       r_sh[i] = ld8_raw(mrow + d.Ip + col);
-      r_s1d[i] = ld8_raw(a.md + b * d.Mp + col);
-      r_shd[i] = ld8_raw(a.md + b * d.Mp + d.Ip + col);
     }
   }
   const float inv_i = 1.0f / (float)d.I;
@@ -490,6 +488,14 @@ __global__ void __launch_bounds__(256) lnmod_vec_kernel(LnModArgs a, Dims d, int
     mean_ncd = warp_sum(acc) * inv_i;
   }
   if (lane == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
+  if (TANGENT) {   // second (and last) batch of loads: the tangent modulation vectors
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = 8 * (lane + 32 * i);
+      r_s1d[i] = ld8_raw(a.md + b * d.Mp + col);
+      r_shd[i] = ld8_raw(a.md + b * d.Mp + d.Ip + col);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = 8 * (lane + 32 * i);
