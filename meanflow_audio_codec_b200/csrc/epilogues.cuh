@@ -110,6 +110,26 @@ struct EpiMulDgelu {
     st_bf4(out + at, mul_dgelu_fast4(acc, av));
   }
 };
+// Column-sum variants (backward: the bias gradient is the column sum of the tensor the epilogue writes).  frag() returns
+// the fp32 values it stored; the epilogue driver (gemm.cuh, epi_colsum) adds them up over the warp's 32 rows and hands
+// one float4 per 4 columns to col_add(), which accumulates it into the fp32 bias gradient with red.global.add.
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  } else {
+    atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+  }
+}
+struct EpiMulDgeluColsum : EpiMulDgelu {
+  static constexpr bool kColSum = true;
+  float* colsum;   // [N] fp32, accumulated
+  __device__ __forceinline__ float4 frag(int row, int col, float4 acc, const Regs& r, const ColRegs&) const {
+    const float4 v = mul_dgelu_fast4(acc, bf4_to_f4(r.av));
+    st_bf4(out + (int64_t)row * ld + col, v);
+    return v;
+  }
+  __device__ __forceinline__ void col_add(int col, float4 v) const { red_add_f4(colsum + col, v); }
+};
 // out = acc (+ bias)
 struct EpiLinearBf16 {
   static constexpr const char* name = "linear_bf16";
@@ -126,6 +146,16 @@ struct EpiLinearBf16 {
   __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
     st_bf4(out + (int64_t)row * ld + col, add4(acc, c.b));
   }
+};
+struct EpiLinearBf16Colsum : EpiLinearBf16 {
+  static constexpr bool kColSum = true;
+  float* colsum;   // [N] fp32, accumulated
+  __device__ __forceinline__ float4 frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
+    const float4 v = add4(acc, c.b);
+    st_bf4(out + (int64_t)row * ld + col, v);
+    return v;
+  }
+  __device__ __forceinline__ void col_add(int col, float4 v) const { red_add_f4(colsum + col, v); }
 };
 struct EpiLinearF32 {
   static constexpr const char* name = "linear_f32";

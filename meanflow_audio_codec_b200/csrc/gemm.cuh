@@ -30,6 +30,7 @@
 #pragma once
 
 #include <cmath>
+#include <type_traits>
 
 #include "mfac_common.cuh"
 
@@ -127,6 +128,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const Epi& epi, const GemmShap
   }
 }
 
+// Functors with Epi::kColSum also want the column sums of what they store (bias gradients).
+template <class E, class = void>
+struct epi_colsum : std::false_type {};
+template <class E>
+struct epi_colsum<E, std::void_t<decltype(E::kColSum)>> : std::bool_constant<E::kColSum> {};
+
 // One epilogue warp's share of one output tile: 32 rows (its TMEM lane quarter) x every other 32-column chunk.
 // FULL = the tile lies entirely inside the matrix (no row / column predicates in the hot loop).
 // The functor's global operands are fetched (coalesced) TWO chunks ahead into two register sets: the first two
@@ -191,12 +198,30 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmShape& s
     for (int p = 0; p < 8; ++p)
       st[lane * 8 + (p ^ (lane & 7))] = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
     __syncwarp();
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = 4 * i + fr;
       const float4 u = st[r * 8 + (fp ^ (r & 7))];
-      if (FULL || (row0 + r < shape.M && col0 + 4 * fp < shape.N))
-        epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
+      if (FULL || (row0 + r < shape.M && col0 + 4 * fp < shape.N)) {
+        if constexpr (epi_colsum<Epi>::value) {
+          const float4 v = epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
+          csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+        } else {
+          epi.frag(row0 + r, col0 + 4 * fp, u, regs[j % DEPTH][i], cregs[j % DEPTH]);
+        }
+      }
+    }
+    if constexpr (epi_colsum<Epi>::value) {
+      // lanes l, l^8, l^16, l^24 hold the same 4 columns of different rows: fold them, one atomic float4 per 32 rows
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+        csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+        csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+      }
+      if (fr == 0 && (FULL || col0 + 4 * fp < shape.N)) epi.col_add(col0 + 4 * fp, csum);
     }
     if (j + DEPTH < NCH) {
       const int coln = col0 + 64 * DEPTH;

@@ -459,16 +459,32 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
         p.g_x, sb.m, sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B);
     count_launch();
     MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
-    MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
+    // Unpadded geometries: the dX epilogues that write g_a and g_shift also accumulate their column sums (db1 and the shift
+    // third of dbc2) -- no separate pass over those tensors.
+    const bool fused_colsum = d.I == d.Ip;
+    if (fused_colsum) {
+      EpiMulDgeluColsum ep;
+      ep.a = sb.a; ep.out = p.g_a; ep.ld = d.Ip; ep.colsum = gk + d.o_m1b;
+      MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, ep, s));
+    } else {
+      MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
+    }
     MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
-    MFAC_OK(colsum(p.g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, s));
+    if (!fused_colsum) MFAC_OK(colsum(p.g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, s));
     // g_hin = g_a W1^T goes out in bf16 straight into g_m[:, Ip:2Ip]: it IS the shift gradient (hin = (1+s1) n + shift)
-    MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
+    if (fused_colsum) {
+      EpiLinearBf16Colsum ep;
+      ep.bias = nullptr; ep.out = p.g_m + d.Ip; ep.ld = d.Mp; ep.colsum = gk + d.o_c2b + d.I;
+      MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, ep, s));
+    } else {
+      MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
+    }
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
     MFAC_OK(gemm_dw(sb.gc, d.Ca, p.g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
-    MFAC_OK(colsum(p.g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, s, 2 * d.Ip));  // s1 | shift thirds
+    // s1 third (and the shift third where it was not fused above)
+    MFAC_OK(colsum(p.g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, s, fused_colsum ? d.Ip : 2 * d.Ip));
     MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac + k * d.Cp, d.Ca}, s));
     if (k == 0) {
       // first modulation layer, all blocks at once: dW = cond^T @ g_ac_all, db = column sums

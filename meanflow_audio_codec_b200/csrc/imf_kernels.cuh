@@ -124,12 +124,29 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
   __syncthreads();
   const float t = s_tr[0], r = s_tr[1];
   const float nscale = a.cfg.noise_min + a.cfg.noise_max * t;
+  const bool vec = d.D == d.Dp && (d.D & 3) == 0;   // unpadded rows: 16-byte accesses (row bases are then 16-byte aligned)
   for (int j4 = threadIdx.x * 4; j4 < d.Dp; j4 += blockDim.x * 4) {
     float ev[4] = {0.f, 0.f, 0.f, 0.f};
     if (!a.e_in && j4 < d.D) {
       const uint64_t idx = ((a.cfg.row_offset + (uint64_t)b) * (uint64_t)d.Dp + (uint64_t)j4) >> 2;
       const float4 n4 = philox_normal4(idx, 0u, a.cfg.seed, step);
       ev[0] = n4.x; ev[1] = n4.y; ev[2] = n4.z; ev[3] = n4.w;
+    }
+    if (vec) {
+      const int64_t at = b * d.Dp + j4;
+      const float4 xv = *reinterpret_cast<const float4*>(a.x + at);
+      const float4 e = a.e_in ? *reinterpret_cast<const float4*>(a.e_in + at) : make_float4(ev[0], ev[1], ev[2], ev[3]);
+      const float omt = 1.0f - t;
+      const float4 zt = make_float4(omt * xv.x + nscale * e.x, omt * xv.y + nscale * e.y, omt * xv.z + nscale * e.z,
+                                    omt * xv.w + nscale * e.w);
+      *reinterpret_cast<float4*>(a.e + at) = e;
+      if (a.z) *reinterpret_cast<float4*>(a.z + at) = zt;
+      *reinterpret_cast<float4*>(a.z2 + at) = zt;
+      if (a.seed)
+        *reinterpret_cast<float4*>(a.seed + at) = make_float4(a.cfg.noise_max * e.x - xv.x, a.cfg.noise_max * e.y - xv.y,
+                                                              a.cfg.noise_max * e.z - xv.z, a.cfg.noise_max * e.w - xv.w);
+      *reinterpret_cast<uint2*>(a.xb + at) = make_uint2(pack_bf16(xv.x, xv.y), pack_bf16(xv.z, xv.w));
+      continue;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -270,22 +287,39 @@ struct LossArgs {
   int64_t B;
 };
 __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims d) {
-  extern __shared__ float s_delta[];  // [Dp]
+  extern __shared__ __align__(16) float s_delta[];  // [Dp]
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
   // MeanFlowLoss clips (t - r) to [0, 1] (loss_strategies.py:178); ImprovedMeanFlowLoss does not (:270)
   float tr = a.t[b] - a.r[b];
   if (a.cfg.method == MFAC_LOSS_MEAN_FLOW) tr = fminf(fmaxf(tr, 0.f), 1.f);
   float sq = 0.f;
-  for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) {
-    float dl = 0.f;
-    if (j < d.D) {
+  const bool vec = d.D == d.Dp && (d.D & 3) == 0;   // unpadded rows: 16-byte accesses
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < d.Dp; j += blockDim.x * 4) {
       const int64_t i = b * d.Dp + j;
-      const float vpred = a.dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
-      dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
+      float4 vp = *reinterpret_cast<const float4*>(a.u + i);
+      if (a.dudt) {
+        const float4 dd = *reinterpret_cast<const float4*>(a.dudt + i);
+        vp.x += tr * dd.x; vp.y += tr * dd.y; vp.z += tr * dd.z; vp.w += tr * dd.w;
+      }
+      const float4 e = *reinterpret_cast<const float4*>(a.e + i), xv = *reinterpret_cast<const float4*>(a.x + i);
+      const float4 dl = make_float4(vp.x - (a.cfg.noise_max * e.x - xv.x), vp.y - (a.cfg.noise_max * e.y - xv.y),
+                                    vp.z - (a.cfg.noise_max * e.z - xv.z), vp.w - (a.cfg.noise_max * e.w - xv.w));
+      *reinterpret_cast<float4*>(s_delta + j) = dl;
+      sq += dl.x * dl.x + dl.y * dl.y + dl.z * dl.z + dl.w * dl.w;
     }
-    s_delta[j] = dl;
-    sq += dl * dl;
+  } else {
+    for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) {
+      float dl = 0.f;
+      if (j < d.D) {
+        const int64_t i = b * d.Dp + j;
+        const float vpred = a.dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
+        dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
+      }
+      s_delta[j] = dl;
+      sq += dl * dl;
+    }
   }
   const float s = block_sum(sq, red);
   float w, rl;
@@ -307,7 +341,14 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
     a.row_loss[b] = rl;
     if (a.per_example) a.per_example[b] = s;
   }
-  for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) a.g_x[b * d.Dp + j] = w * s_delta[j];
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < d.Dp; j += blockDim.x * 4) {
+      const float4 dl = *reinterpret_cast<const float4*>(s_delta + j);
+      *reinterpret_cast<float4*>(a.g_x + b * d.Dp + j) = make_float4(w * dl.x, w * dl.y, w * dl.z, w * dl.w);
+    }
+  } else {
+    for (int j = threadIdx.x; j < d.Dp; j += blockDim.x) a.g_x[b * d.Dp + j] = w * s_delta[j];
+  }
 }
 // deterministic sum of row_loss[B] -> loss
 __global__ void __launch_bounds__(1024) sum_rows_kernel(const float* v, int64_t n, float* out) {
