@@ -267,6 +267,8 @@ MFAC_API int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int
                          int32_t a_mn_major, int32_t b_mn_major, int32_t block_n, void* stream);
 /* 1 = route every GEMM through a plain SIMT kernel (debug triage only; never set in product use). */
 MFAC_API int mfac_debug_set_simt_gemm(int32_t on);
+/* 0 = slice K uniformly for the weight-gradient GEMMs; 1 (default) = stream-K (equal contiguous k-block ranges per CTA pair). */
+MFAC_API int mfac_debug_set_stream_k(int32_t on);
 /* 0 = never use the CTA-pair (cta_group::2) GEMM kernel; 1 (default) = use it where it pays. */
 MFAC_API int mfac_debug_set_pair_gemm(int32_t on);
 MFAC_API int mfac_debug_counters(int64_t* kernel_launches);

@@ -110,6 +110,7 @@ PROTOTYPES = {
     "mfac_debug_gemm_bf16": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
     "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
     "mfac_debug_set_pair_gemm": (C.c_int, [_I32]),
+    "mfac_debug_set_stream_k": (C.c_int, [_I32]),
     "mfac_debug_counters": (C.c_int, [C.POINTER(_I64)]),
     "mfac_profile_enable": (C.c_int, [_I32]),
     "mfac_profile_collect": (C.c_int, [C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -419,6 +419,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   tfull[a]  one per CTA, same multicast commit: the accumulator of buffer a is complete in both TMEMs
 //   tempty[a] lives in the leader and counts the epilogue warps of BOTH CTAs (the peer's arrive remotely)
 // ---------------------------------------------------------------------------------------
+// Work decomposition of one CTA pair.  Uniform mode (shape.splits >= 1): items (tile, k-slice) strided over the pairs.
+// Stream-K mode (shape.splits == 0, weight gradients): the tiles' k-blocks form one line of tiles * k_blocks entries that is
+// cut into equal contiguous ranges, one per pair; a range crosses at most one tile boundary per k_blocks entries, so every
+// pair does the same number of MMAs (no wave quantisation) and the number of partial tiles that go through the atomic
+// epilogue drops from tiles * splits to about pairs + tiles.
+struct Seg { int tile, kb0, kb1; };
+struct SegIter {
+  int item, stride, num_items, splits, kbps, kbt;   // uniform
+  int g, g_end;                                     // stream-K
+  __device__ __forceinline__ SegIter(const GemmShape& sh, int tiles, int kbt_, int pair, int npairs)
+      : item(pair), stride(npairs), num_items(tiles * sh.splits), splits(sh.splits), kbps(sh.kb_per_split), kbt(kbt_), g(0), g_end(0) {
+    if (splits == 0) {
+      const int total = tiles * kbt, q = (total + npairs - 1) / npairs;
+      g = pair * q < total ? pair * q : total;
+      g_end = g + q < total ? g + q : total;
+    }
+  }
+  __device__ __forceinline__ bool next(Seg& o) {
+    if (splits == 0) {
+      if (g >= g_end) return false;
+      o.tile = g / kbt;
+      o.kb0 = g - o.tile * kbt;
+      o.kb1 = o.kb0 + (g_end - g) < kbt ? o.kb0 + (g_end - g) : kbt;
+      g += o.kb1 - o.kb0;
+      return true;
+    }
+    if (item >= num_items) return false;
+    o.tile = item / splits;
+    o.kb0 = (item - o.tile * splits) * kbps;
+    o.kb1 = o.kb0 + kbps < kbt ? o.kb0 + kbps : kbt;
+    item += stride;
+    return true;
+  }
+  // tile of the segment after the current one, or -1 (uniform mode only: the look-ahead drives the L2 operand prefetch)
+  __device__ __forceinline__ int peek_tile() const { return (splits != 0 && item < num_items) ? item / splits : -1; }
+};
+
 constexpr int GEMM2_BN = 256;
 struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // this CTA's 128 rows
@@ -458,7 +495,6 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int m_tiles = ceil_div(shape.M, 2 * GEMM_BM);  // 256-row pair tiles
   const int n_tiles = ceil_div(shape.N, BN);
   const int k_blocks_total = ceil_div(shape.K, GEMM_BK);
-  const int num_items = m_tiles * n_tiles * shape.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -487,12 +523,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
     if (lane == 0) {
       uint32_t kit = 0;
-      for (int item = pair; item < num_items; item += npairs) {
-        const int tile = item / shape.splits, sp = item % shape.splits;
+      SegIter segs(shape, m_tiles * n_tiles, k_blocks_total, pair, npairs);
+      Seg sg;
+      while (segs.next(sg)) {
+        const int tile = sg.tile;
         const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;   // this CTA's rows
         const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);           // this CTA's half of the columns
-        const int kb0 = sp * shape.kb_per_split;
-        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         for (int kb = kb0; kb < kb1; ++kb, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1;
@@ -523,10 +560,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, A_MN, B_MN);
       uint32_t kit = 0, it = 0;
-      for (int item = pair; item < num_items; item += npairs, ++it) {
-        const int sp = item % shape.splits;
-        const int kb0 = sp * shape.kb_per_split;
-        const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
+      SegIter segs(shape, m_tiles * n_tiles, k_blocks_total, pair, npairs);
+      Seg sg;
+      for (; segs.next(sg); ++it) {
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         const uint32_t as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
@@ -563,21 +600,22 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float4* st = reinterpret_cast<float4*>(sStage + (warp - 4) * 4096);
     uint32_t it = 0;
     const uint32_t lead_tempty0 = mapa_u32(&tempty_bar[0], 0), lead_tempty1 = mapa_u32(&tempty_bar[1], 0);
-    if (pair < num_items) {
-      const int tile = pair / shape.splits;
-      epi.prefetch((tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
+    SegIter segs(shape, m_tiles * n_tiles, k_blocks_total, pair, npairs);
+    Seg sg;
+    {
+      const int tile = segs.peek_tile();
+      if (tile >= 0)
+        epi.prefetch((tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
     }
-    for (int item = pair; item < num_items; item += npairs, ++it) {
-      const int tile = item / shape.splits;
+    for (; segs.next(sg); ++it) {
+      const int tile = sg.tile;
       const uint32_t as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
-      if (item + npairs < num_items) {
-        const int nt = (item + npairs) / shape.splits;
-        if (nt != tile)
-          epi.prefetch((nt / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
-      }
+      const int nt = segs.peek_tile();
+      if (nt >= 0 && nt != tile)
+        epi.prefetch((nt / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
       epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
       tc_fence_before();
@@ -701,6 +739,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
 }
 
 bool pair_gemm_enabled();   // runtime.cu: on unless MFAC_NO_PAIR_GEMM is set / mfac_debug_set_pair_gemm(0)
+bool stream_k_enabled();    // runtime.cu: on unless MFAC_NO_STREAM_K is set
 
 // CTA pairs pay for compute-bound shapes that fill the machine with whole 256 x 256 tiles.
 inline bool pair_gemm_pays(int M, int N, int K, bool split_k) {
@@ -751,9 +790,20 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
       if (eff > best) { best = eff; splits = sp; }
     }
   }
-  const int kbps = ceil_div(k_blocks, splits);
+  int kbps = ceil_div(k_blocks, splits);
   splits = ceil_div(k_blocks, kbps);
-  const int items = tiles * splits;
+  int items = tiles * splits;
+  const double uniform_waves = (double)items / pairs;
+  if (split_k && stream_k_enabled() && (int64_t)tiles * k_blocks >= 4 * (int64_t)pairs &&
+      uniform_waves / std::ceil(uniform_waves) < 0.97) {
+    // stream-K (see SegIter): every pair gets the same number of k-blocks.  Only where the best uniform slicing leaves a
+    // ragged last wave: concurrent uniform items walk the same k-slice of neighbouring tiles and share those operand
+    // panels in L2, stream-K ranges do not (measured at 18944 rows: 1280x1024 47 us uniform / 57 us stream-K,
+    // 1280x1280 76 us uniform (4.73 waves) / 64 us stream-K).
+    splits = 0;
+    kbps = 0;
+    items = pairs;
+  }
   const int grid = 2 * (items < pairs ? items : pairs);
   GemmShape shape{M, N, K, splits, kbps};
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
@@ -798,7 +848,7 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
   if (split_k) {
     // Weight gradients: few output tiles, K = batch.  Pick the slice count whose (tiles x slices) work
     // items fill whole waves of the machine best, with at least 4 k-blocks per item.
-    bn = force_bn ? force_bn : 128;
+    bn = force_bn ? force_bn : 128;   // (256-wide tiles measured slower for the [C, 2I+D] modulation gradient: 9.16 vs 9.02 ms/step)
     const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
     const int k_blocks = ceil_div(K, GEMM_BK);
     double best = -1.0;

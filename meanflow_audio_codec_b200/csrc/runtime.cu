@@ -14,6 +14,7 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_simt{0};
 std::atomic<int> g_pair{getenv("MFAC_NO_PAIR_GEMM") ? 0 : 1};
+std::atomic<int> g_streamk{getenv("MFAC_NO_STREAM_K") ? 0 : 1};
 std::atomic<int> g_num_sms{0};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -65,6 +66,7 @@ void profile_end(void* token, cudaStream_t s) {
 }
 bool simt_gemm_enabled() { return g_simt.load(std::memory_order_relaxed) != 0; }
 bool pair_gemm_enabled() { return g_pair.load(std::memory_order_relaxed) != 0; }
+bool stream_k_enabled() { return g_streamk.load(std::memory_order_relaxed) != 0; }
 
 int num_sms() {
   int n = g_num_sms.load(std::memory_order_relaxed);
@@ -136,6 +138,11 @@ int mfac_debug_gemm_bf16(const void* A, const void* B, float* Cout, int64_t M, i
 
 int mfac_debug_set_simt_gemm(int32_t on) {
   mfac::g_simt.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+int mfac_debug_set_stream_k(int32_t on) {
+  mfac::g_streamk.store(on ? 1 : 0);
   return MFAC_SUCCESS;
 }
 

@@ -417,3 +417,33 @@ def test_shared_pass_for_rows_with_r_equal_t(setup):
     assert torch.equal(b0["t"][:hrows], b0["r"][:hrows])
     for k in ("e", "t", "r", "v", "u", "dudt", "per_example"):
         assert torch.equal(b0[k], b1[k]), k
+
+
+@pytest.mark.parametrize("B", [1000, 4096])
+def test_stream_k_weight_gradients_match_uniform_split_k(cuda, B):
+    """The weight-gradient GEMMs cut the (tile, k-block) line into equal contiguous ranges per CTA pair (stream-K).  Same
+    products, same fp32 atomics as the uniform k-slices: the gradients agree to summation-order noise, for whole and
+    ragged (B = 1000: partial last k-block, ranges that cross tile boundaries) batches."""
+    import meanflow_audio_codec_b200 as m
+    from meanflow_audio_codec_b200 import _lib
+    D, L, C, nb = 1024, 256, 128, 2
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=model.init(1)["params"], tx=m.adamw(1e-4, 1e-4))
+    strat = m.ImprovedMeanFlowLoss()
+    x = 2 * torch.rand(B, D, device="cuda") - 1
+    try:
+        _lib.lib().mfac_debug_set_stream_k(0)
+        l0, g0 = strat.compute_loss(state, 3, x)
+        g0 = g0.flat.clone()
+        _lib.lib().mfac_debug_set_stream_k(1)
+        l1, g1 = strat.compute_loss(state, 3, x)
+    finally:
+        _lib.lib().mfac_debug_set_stream_k(1)
+    assert float(l0) == float(l1)
+    assert float((g1.flat - g0).norm() / g0.norm()) < 1e-5
+    sl = model.leaf_slices()
+    for path in (("blocks_1", "mlp", "dense1", "kernel"), ("blocks_0", "mlp", "dense2", "kernel")):
+        off, shp = sl[path]
+        n = shp[0] * shp[1]
+        a, b = g1.flat[off:off + n], g0[off:off + n]
+        assert float((a - b).norm() / b.norm()) < 1e-5, path
