@@ -76,7 +76,16 @@ struct GemmShape {
   int M, N, K;
   int splits;        // split-K factor (1 = none); work item = tile * splits + split
   int kb_per_split;  // 64-wide k-blocks per split
+  int no_prefetch;   // 1 = skip the one-tile-ahead L2 prefetch of the epilogue operands (the default, see below)
 };
+// The L2 prefetch of the next tile's epilogue operands paid while the epilogues were latency-bound; with the current
+// register prefetch it only adds DRAM traffic (lines fetched early are evicted before use: 371 MB read against 294 MB of
+// unique bytes in the tangent block-output GEMM) -- measured at 18944 rows: block_out 58 -> 51 us, block_out_tangent
+// 98 -> 83 us, step 9.05 -> 8.89 ms without it.  MFAC_EPI_PREFETCH=1 switches it back on.
+inline int epi_prefetch_off() {
+  static const int off = getenv("MFAC_EPI_PREFETCH") ? 0 : 1;
+  return off;
+}
 
 // Output tensor maps of the TMA-store epilogues (bf16 outputs, 32 x 32 boxes, 64-byte swizzle)
 struct EpiTmaps {
@@ -370,7 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // tile's are requested one tile ahead (the register prefetch inside a tile then only sees L2 latency).
     if ((int)blockIdx.x < num_items) {
       const int tile = blockIdx.x / shape.splits;
-      epi.prefetch((tile / n_tiles) * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
+      if (!shape.no_prefetch) epi.prefetch((tile / n_tiles) * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
     }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int tile = item / shape.splits;
@@ -380,7 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile % n_tiles) * BN;
       if (item + (int)gridDim.x < num_items) {
         const int nt = (item + gridDim.x) / shape.splits;
-        if (nt != tile) epi.prefetch((nt / n_tiles) * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
+        if (nt != tile && !shape.no_prefetch) epi.prefetch((nt / n_tiles) * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
       }
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
       if constexpr (Epi::kTmaStore)
@@ -604,7 +613,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     Seg sg;
     {
       const int tile = segs.peek_tile();
-      if (tile >= 0)
+      if (tile >= 0 && !shape.no_prefetch)
         epi.prefetch((tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
     }
     for (; segs.next(sg); ++it) {
@@ -614,7 +623,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int nt = segs.peek_tile();
-      if (nt >= 0 && nt != tile)
+      if (nt >= 0 && nt != tile && !shape.no_prefetch)
         epi.prefetch((nt / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (nt % n_tiles) * BN, BN, shape.M, shape.N, etid);
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
       epilogue_tile<BN, FULL>(epi, shape, st, taddr, m0 + quarter * 32, n0, half, lane, &tfull_bar[as], aph);
@@ -723,7 +732,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   splits = ceil_div(k_blocks, kbps);  // no empty slice
   const int items = tiles * splits;
   const int grid = items < num_sms() ? items : num_sms();
-  GemmShape shape{M, N, K, splits, kbps};
+  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off()};
   EpiTmaps maps;
   if constexpr (Epi::kTmaStore) {
     MFAC_OK(epi.make_maps(maps, M, N));
@@ -805,7 +814,7 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
     items = pairs;
   }
   const int grid = 2 * (items < pairs ? items : pairs);
-  GemmShape shape{M, N, K, splits, kbps};
+  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off()};
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
   profile_end(prof, stream);
@@ -827,7 +836,7 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
     SimtOperand a{reinterpret_cast<const __nv_bfloat16*>(A.ptr), A.ld, A_MN ? 1 : 0};
     SimtOperand b{reinterpret_cast<const __nv_bfloat16*>(B.ptr), B.ld, B_MN ? 1 : 0};
     const int64_t threads = (int64_t)M * (N / 32);
-    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K, 1, 0}, epi);
+    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K, 1, 0, 0}, epi);
     count_launch();
     return launch_status();
   }
