@@ -76,15 +76,16 @@ struct GemmShape {
   int M, N, K;
   int splits;        // split-K factor (1 = none); work item = tile * splits + split
   int kb_per_split;  // 64-wide k-blocks per split
-  int no_prefetch;   // 1 = skip the one-tile-ahead L2 prefetch of the epilogue operands (the default, see below)
+  int no_prefetch;   // L2 prefetch of the epilogue operands: 0 = first tile + one tile ahead, 1 = first tile only, 2 = none (default)
 };
 // The L2 prefetch of the next tile's epilogue operands paid while the epilogues were latency-bound; with the current
 // register prefetch it only adds DRAM traffic (lines fetched early are evicted before use: 371 MB read against 294 MB of
 // unique bytes in the tangent block-output GEMM) -- measured at 18944 rows: block_out 58 -> 51 us, block_out_tangent
-// 98 -> 83 us, step 9.05 -> 8.89 ms without it.  MFAC_EPI_PREFETCH=1 switches it back on.
+// 98 -> 83 us, step 9.02 -> 8.81 ms without it.  MFAC_EPI_PREFETCH=2 switches it back on.
+// (first-tile-only prefetch: 8.88 ms, none: 8.81 ms; 1024 and 4096 rows are indifferent.)
 inline int epi_prefetch_off() {
-  static const int off = getenv("MFAC_EPI_PREFETCH") ? 0 : 1;
-  return off;
+  static const int off = getenv("MFAC_EPI_PREFETCH") ? 2 - atoi(getenv("MFAC_EPI_PREFETCH")) : 2;   // env 2 -> all, 1 -> first tile, 0 -> none
+  return off < 0 ? 0 : (off > 2 ? 2 : off);
 }
 
 // Output tensor maps of the TMA-store epilogues (bf16 outputs, 32 x 32 boxes, 64-byte swizzle)
@@ -379,7 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // tile's are requested one tile ahead (the register prefetch inside a tile then only sees L2 latency).
     if ((int)blockIdx.x < num_items) {
       const int tile = blockIdx.x / shape.splits;
-      if (!shape.no_prefetch) epi.prefetch((tile / n_tiles) * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
+      if (shape.no_prefetch < 2) epi.prefetch((tile / n_tiles) * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
     }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int tile = item / shape.splits;
@@ -613,7 +614,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     Seg sg;
     {
       const int tile = segs.peek_tile();
-      if (tile >= 0 && !shape.no_prefetch)
+      if (tile >= 0 && shape.no_prefetch < 2)
         epi.prefetch((tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM, (tile % n_tiles) * BN, BN, shape.M, shape.N, etid);
     }
     for (; segs.next(sg); ++it) {
@@ -803,12 +804,13 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
   splits = ceil_div(k_blocks, kbps);
   int items = tiles * splits;
   const double uniform_waves = (double)items / pairs;
-  if (split_k && stream_k_enabled() && (int64_t)tiles * k_blocks >= 4 * (int64_t)pairs &&
+  if (split_k && stream_k_enabled() && (int64_t)tiles * k_blocks >= 8 * (int64_t)pairs &&
       uniform_waves / std::ceil(uniform_waves) < 0.97) {
     // stream-K (see SegIter): every pair gets the same number of k-blocks.  Only where the best uniform slicing leaves a
     // ragged last wave: concurrent uniform items walk the same k-slice of neighbouring tiles and share those operand
     // panels in L2, stream-K ranges do not (measured at 18944 rows: 1280x1024 47 us uniform / 57 us stream-K,
-    // 1280x1280 76 us uniform (4.73 waves) / 64 us stream-K).
+    // 1280x1280 76 us uniform (4.73 waves) / 64 us stream-K).  Below ~8 k-blocks per pair the ranges are too short to pay
+    // (1024 rows: 2.42 ms/step uniform, 2.59 stream-K; 2048 rows: 2.95 / 2.84).
     splits = 0;
     kbps = 0;
     items = pairs;
