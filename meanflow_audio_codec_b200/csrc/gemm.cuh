@@ -77,7 +77,20 @@ struct GemmShape {
   int splits;        // split-K factor (1 = none); work item = tile * splits + split
   int kb_per_split;  // 64-wide k-blocks per split
   int no_prefetch;   // L2 prefetch of the epilogue operands: 0 = first tile + one tile ahead, 1 = first tile only, 2 = none (default)
+  int reverse_m;     // 1 = walk the row tiles from the last to the first (the rows the previous kernel touched last are
+                     // the ones still in L2)
 };
+// Sweep direction of the next row-parallel kernel (GEMMs without split-K and the vectorised row kernels): consecutive
+// kernels of a chain alternate between ascending and descending rows, so that each one starts on the rows its producer
+// touched last -- the part of the producer's output that is still in the 126 MB L2 (the step's tensors are 40-270 MB each).
+// Results do not depend on the direction.  MFAC_NO_SWEEP_ALTERNATE=1 keeps every kernel ascending.
+inline int sweep_next() {
+  static const int on = getenv("MFAC_NO_SWEEP_ALTERNATE") ? 0 : 1;
+  static thread_local int cur = 0;
+  if (!on) return 0;
+  cur ^= 1;
+  return cur;
+}
 // The L2 prefetch of the next tile's epilogue operands paid while the epilogues were latency-bound; with the current
 // register prefetch it only adds DRAM traffic (lines fetched early are evicted before use: 371 MB read against 294 MB of
 // unique bytes in the tangent block-output GEMM) -- measured at 18944 rows: block_out 58 -> 51 us, block_out_tangent
@@ -302,7 +315,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t kit = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int tile = item / shape.splits, sp = item % shape.splits;
-        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int m0 = (shape.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
         const int kb0 = sp * shape.kb_per_split;
         const int kb1 = min(k_blocks_total, kb0 + shape.kb_per_split);
@@ -386,7 +399,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int tile = item / shape.splits;
       const uint32_t as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int m0 = (shape.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       if (item + (int)gridDim.x < num_items) {
         const int nt = (item + gridDim.x) / shape.splits;
@@ -537,7 +550,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       Seg sg;
       while (segs.next(sg)) {
         const int tile = sg.tile;
-        const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;   // this CTA's rows
+        const int m0 = (shape.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;   // this CTA's rows
         const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);           // this CTA's half of the columns
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         for (int kb = kb0; kb < kb1; ++kb, ++kit) {
@@ -621,7 +634,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int tile = sg.tile;
       const uint32_t as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      const int m0 = (shape.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles) * 2 * GEMM_BM + (int)rank * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int nt = segs.peek_tile();
       if (nt >= 0 && nt != tile && !shape.no_prefetch)
@@ -733,7 +746,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   splits = ceil_div(k_blocks, kbps);  // no empty slice
   const int items = tiles * splits;
   const int grid = items < num_sms() ? items : num_sms();
-  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off()};
+  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off(), splits != 1 ? 0 : sweep_next()};
   EpiTmaps maps;
   if constexpr (Epi::kTmaStore) {
     MFAC_OK(epi.make_maps(maps, M, N));
@@ -816,7 +829,7 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
     items = pairs;
   }
   const int grid = 2 * (items < pairs ? items : pairs);
-  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off()};
+  GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off(), splits != 1 ? 0 : sweep_next()};
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
   profile_end(prof, stream);
@@ -838,7 +851,7 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
     SimtOperand a{reinterpret_cast<const __nv_bfloat16*>(A.ptr), A.ld, A_MN ? 1 : 0};
     SimtOperand b{reinterpret_cast<const __nv_bfloat16*>(B.ptr), B.ld, B_MN ? 1 : 0};
     const int64_t threads = (int64_t)M * (N / 32);
-    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K, 1, 0, 0}, epi);
+    gemm_simt_kernel<Epi><<<(unsigned)ceil_div<int64_t>(threads, 128), 128, 0, stream>>>(a, b, GemmShape{M, N, K, 1, 0, 0, 0}, epi);
     count_launch();
     return launch_status();
   }

@@ -66,7 +66,9 @@ inline int vec_rows(const Dims& d) {
   return d.Ip / 256;
 }
 
-int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
+int lnmod(bool tangent, const LnModArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
+  LnModArgs a = a_in;
+  a.reverse = vec_rows(d) ? sweep_next() : 0;
   const size_t smem = (size_t)d.Ip * 4 * (tangent ? 2 : 1);
   if (smem > 200 * 1024) return MFAC_ERR_UNSUPPORTED;
   static bool configured = false;
@@ -97,7 +99,9 @@ int lnmod(bool tangent, const LnModArgs& a, const Dims& d, int64_t B, cudaStream
   return launch_status();
 }
 
-int ln_bwd(const LnBwdArgs& a, const Dims& d, int64_t B, cudaStream_t s) {
+int ln_bwd(const LnBwdArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
+  LnBwdArgs a = a_in;
+  a.reverse = vec_rows(d) ? sweep_next() : 0;
   const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 4);   // ~200 registers per thread: 4-row CTAs, two per SM
 #define MFAC_LNBWD_CASE(NVV) case NVV: ln_bwd_vec_kernel<NVV><<<vgrid, 128, 0, s>>>(a, d, B); break;
   switch (vec_rows(d)) {
@@ -456,7 +460,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     const float* x_in = p.xs + (int64_t)k * B * d.Dp;
     // g_o, g_s2 and both of their bias-gradient column sums (db2, the s2 third of dbc2) in one pass
     bwd_block_out_vec_kernel<<<dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), 256, 0, s>>>(
-        p.g_x, sb.m, sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B);
+        p.g_x, sb.m, sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B, sweep_next());
     count_launch();
     MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
     // Unpadded geometries: the dX epilogues that write g_a and g_shift also accumulate their column sums (db1 and the shift

@@ -215,6 +215,7 @@ struct LnModArgs {
   float* rstd;               // [B] or null
   int64_t m_stride;          // row stride of m in elements: Mp, or 0 when every row shares one modulation row
                              // (samplers: the modulation depends on (t, h) only, which is constant over the batch)
+  int reverse;               // vectorised kernels: 1 = CTAs walk the rows from the last to the first (gemm.cuh: sweep_next)
 };
 
 template <bool TANGENT>
@@ -372,6 +373,7 @@ struct LnBwdArgs {
   __nv_bfloat16* g_m;       // [B, Mp]  reads [Ip, 2Ip), writes [0, Ip)
   float* g_lat;             // [B, Lp]  +=
   float* g_x;               // [B, Dp]  +=
+  int reverse;              // vectorised kernel: 1 = CTAs walk the rows from the last to the first
 };
 __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a, Dims d) {
   extern __shared__ float s_row[];  // n[Ip], g_n[Ip]
@@ -474,7 +476,7 @@ __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) 
 template <int NV, bool TANGENT>
 __global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t b = (int64_t)(a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   float c[NV][8], cd[TANGENT ? NV : 1][8];
   float sum = 0.f, sq = 0.f, sumd = 0.f;
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_ve
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, int64_t B) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t b = (int64_t)(a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   // every load of the row is requested before the first store (the stores alias the loads as far as the compiler knows,
   // which would otherwise serialise one memory latency per chunk)
@@ -626,11 +628,11 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
 // grid (Dp/256, ceil(B/256)); thread = 8 columns x every 8th row of a 256-row slab (same shape as the column-sum kernel).
 __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o,
                                                                 __nv_bfloat16* g_o, __nv_bfloat16* g_m, float* db_o, float* db_m,
-                                                                Dims d, int64_t B) {
+                                                                Dims d, int64_t B, int reverse) {
   __shared__ float s_red[2][8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
-  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_VROWS;
+  const int64_t r0 = (int64_t)(reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y) * COLSUM_VROWS;
   const int64_t r1 = min(B, r0 + COLSUM_VROWS);
   const float inv_nb = 1.0f / (float)d.nb;
   float so[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
