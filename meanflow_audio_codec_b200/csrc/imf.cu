@@ -412,37 +412,48 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
       MFAC_OK(lnmod(false, la, d, B, s));
       MFAC_OK(primal_mlp(k, 0, M));
     }
-    MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.xs + (int64_t)d.nb * B * d.Dp, (size_t)B * d.Dp * 4, cudaMemcpyDeviceToDevice, s));
+    // v is the tangent seed of the rows that still get a u pass (and an optional test output for all rows)
+    const int64_t v0 = (aux && aux->v) ? 0 : h;
+    if (v0 < B)
+      MFAC_CUDA_OK(cudaMemcpyAsync(p.v + v0 * d.Dp, p.xs + (int64_t)d.nb * B * d.Dp + v0 * d.Dp, (size_t)(B - v0) * d.Dp * 4,
+                                   cudaMemcpyDeviceToDevice, s));
   } else if (need_v) {
     MFAC_OK(forward_pass(d, sh, p.cond_v, p.lat, p.v, B, p.fs, s));
   }
-  // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))
+  // ---- (u, du/dt) = jvp(f, (z, [t, t-r]), (v, [1, 1]))  on rows [h, B)
+  // Rows [0, h) are finished: their u is the shared pass's output, and their du/dt is never used -- the loss multiplies it
+  // by (t - r), which is exactly 0 there (v_pred = u + 0 * du/dt = u bit for bit).  Everything below runs on the Mu rows
+  // whose u evaluation differs from their v evaluation.
   // first modulation layer of all blocks, primal and tangent, in two GEMMs
-  if (Mu > 0)
+  if (Mu > 0) {
     MFAC_OK(gemm_bias_gelu(p.cond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all + h * d.Ca,
                            p.ac_all + h * d.Ca, d.Ca, s));
-  if (tangent) MFAC_OK(gemm_fwd(p.dcond_u, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, EpiMulDgelu{p.ac_all, p.gcd, d.Ca}, s));
-  for (int k = 0; k < d.nb; ++k) {
+    if (tangent)
+      MFAC_OK(gemm_fwd(p.dcond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp,
+                       EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, s));
+  }
+  for (int k = 0; k < d.nb && Mu > 0; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     SavedBlock& sb = p.blk[k];
-    float* x_in = p.xs + (int64_t)k * B * d.Dp;
-    const float* xd_in = k == 0 ? p.v : p.xd;
-    // modulation, primal (rows [h, B): rows [0, h) keep the shared pass's) and tangent
-    if (Mu > 0) MFAC_OK(primal_mod(k, h, Mu));
-    if (tangent) MFAC_OK(gemm_linear_bf16(p.gcd + k * d.Cp, d.Ca, w + d.s_c2w, M, d.Mp, d.Cp, nullptr, p.md, d.Mp, s));
-    // all rows: rows [0, h) re-derive the same hin / statistics from the same inputs, and get their tangent
-    LnModArgs la{p.lat, x_in, sb.m, sb.hin, xd_in, p.md, p.hind, sb.mu, sb.rstd, d.Mp};
-    MFAC_OK(lnmod(tangent, la, d, B, s));
+    float* x_in = p.xs + (int64_t)k * B * d.Dp + h * d.Dp;
+    const float* xd_in = (k == 0 ? p.v : p.xd) + h * d.Dp;
+    // modulation, primal and tangent
+    MFAC_OK(primal_mod(k, h, Mu));
+    if (tangent)
+      MFAC_OK(gemm_linear_bf16(p.gcd + h * d.Ca + k * d.Cp, d.Ca, w + d.s_c2w, Mu, d.Mp, d.Cp, nullptr, p.md + h * d.Mp, d.Mp, s));
+    LnModArgs la{p.lat + h * d.Lp, x_in, sb.m + h * d.Mp, sb.hin + h * d.Ip, xd_in, p.md + h * d.Mp, p.hind + h * d.Ip,
+                 sb.mu + h, sb.rstd + h, d.Mp};
+    MFAC_OK(lnmod(tangent, la, d, Mu, s));
+    // the tangent GEMMs read the primal pre-activation a and block output o: primal first
+    MFAC_OK(primal_mlp(k, h, Mu));
     if (tangent) {
-      // the tangent GEMMs read the primal pre-activation a and block output o: primal first
-      if (Mu > 0) MFAC_OK(primal_mlp(k, h, Mu));
-      MFAC_OK(gemm_fwd(p.hind, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiMulDgelu{sb.a, p.gd, d.Ip}, s));
-      MFAC_OK(gemm_fwd(p.gd, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
-                       EpiBlockOutTangent{sb.m, p.md, sb.o, xd_in, p.xd, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s));
-    } else {
-      MFAC_OK(primal_mlp(k, 0, M));
+      MFAC_OK(gemm_fwd(p.hind + h * d.Ip, d.Ip, w + d.s_m1w, Mu, d.Ip, d.Ip, EpiMulDgelu{sb.a + h * d.Ip, p.gd + h * d.Ip, d.Ip}, s));
+      MFAC_OK(gemm_fwd(p.gd + h * d.Ip, d.Ip, w + d.s_m2w, Mu, d.Dp, d.Ip,
+                       EpiBlockOutTangent{sb.m + h * d.Mp, p.md + h * d.Mp, sb.o + h * d.Dp, xd_in, p.xd + h * d.Dp, d.Mp, d.Dp,
+                                          2 * d.Ip, inv_nb}, s));
     }
   }
+  if (h > 0 && tangent && aux && aux->dudt) MFAC_CUDA_OK(cudaMemsetAsync(p.xd, 0, (size_t)h * d.Dp * 4, s));  // reported as 0
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
   // ---- loss and its seed gradient
   LossArgs lo{u, tangent ? p.xd : nullptr, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};

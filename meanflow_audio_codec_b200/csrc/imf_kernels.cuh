@@ -296,11 +296,14 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
   if (a.cfg.method == MFAC_LOSS_MEAN_FLOW) tr = fminf(fmaxf(tr, 0.f), 1.f);
   float sq = 0.f;
   const bool vec = d.D == d.Dp && (d.D & 3) == 0;   // unpadded rows: 16-byte accesses
+  // (t - r) == 0 (every r == t row): v_pred = u + 0 * du/dt = u, and du/dt is not read -- the step does not even compute it
+  // for the leading r == t rows (imf.cu)
+  const bool use_dudt = a.dudt != nullptr && tr != 0.f;
   if (vec) {
     for (int j = threadIdx.x * 4; j < d.Dp; j += blockDim.x * 4) {
       const int64_t i = b * d.Dp + j;
       float4 vp = *reinterpret_cast<const float4*>(a.u + i);
-      if (a.dudt) {
+      if (use_dudt) {
         const float4 dd = *reinterpret_cast<const float4*>(a.dudt + i);
         vp.x += tr * dd.x; vp.y += tr * dd.y; vp.z += tr * dd.z; vp.w += tr * dd.w;
       }
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
       float dl = 0.f;
       if (j < d.D) {
         const int64_t i = b * d.Dp + j;
-        const float vpred = a.dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
+        const float vpred = use_dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
         dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
       }
       s_delta[j] = dl;

@@ -388,8 +388,9 @@ def test_checkpoint_resume_continues_bit_identically(cuda, tmp_path):
 
 def test_shared_pass_for_rows_with_r_equal_t(setup):
     """utils.py:41-44 gives the first int(B * data_proportion) rows r = t; on those rows f(z, [t, t - r]) is the v
-    evaluation f(z, [t, 0]), so the step runs ONE saved primal pass for them (MfacImfConfig.rows_r_equals_t).  The
-    shared schedule must give the bits of the plain one (same dot products, same order) and still match the oracle."""
+    evaluation f(z, [t, 0]), so the step runs ONE saved primal pass for them (MfacImfConfig.rows_r_equals_t) and no
+    tangent pass (their du/dt only ever meets the factor (t - r) == 0).  The shared schedule must give the bits of the
+    plain one (same dot products, same order) and still match the oracle."""
     m, model, tree, p_np, (D, L, C, nb, B) = setup
     x, e, t, r = _inputs(D, B)
     hrows = int(B * 0.5)
@@ -400,8 +401,10 @@ def test_shared_pass_for_rows_with_r_equal_t(setup):
     kw = dict(noise=c(e), t=c(t[:, 0]), r=c(r[:, 0]), return_aux=True)
     l0, g0, a0 = strat.compute_loss(state, 0, c(x), **kw)
     l1, g1, a1 = strat.compute_loss(state, 0, c(x), rows_r_equals_t=hrows, **kw)
-    for k in ("v", "u", "dudt", "per_example"):
+    for k in ("v", "u", "per_example"):
         assert torch.equal(a0[k], a1[k]), k
+    # du/dt of the shared rows is multiplied by (t - r) == 0 in the loss: the shared schedule does not compute it (reports 0)
+    assert torch.equal(a0["dudt"][hrows:], a1["dudt"][hrows:]) and not a1["dudt"][:hrows].any()
     assert float(l0) == float(l1)
     f0, f1 = g0.flat.cpu().numpy(), g1.flat.cpu().numpy()
     assert rel_l2(f1, f0) < 1e-5            # split-K partial sums are accumulated atomically: order varies run to run
@@ -415,8 +418,9 @@ def test_shared_pass_for_rows_with_r_equal_t(setup):
     _, _, b0 = strat.compute_loss(state, 9, c(x), return_aux=True, rows_r_equals_t=-1)
     _, _, b1 = strat.compute_loss(state, 9, c(x), return_aux=True)
     assert torch.equal(b0["t"][:hrows], b0["r"][:hrows])
-    for k in ("e", "t", "r", "v", "u", "dudt", "per_example"):
+    for k in ("e", "t", "r", "v", "u", "per_example"):
         assert torch.equal(b0[k], b1[k]), k
+    assert torch.equal(b0["dudt"][hrows:], b1["dudt"][hrows:]) and not b1["dudt"][:hrows].any()
 
 
 @pytest.mark.parametrize("B", [2500, 4096])
