@@ -11,8 +11,9 @@ JVP, loss, backward) -> gradient all-reduce (N > 1) -> AdamW.  Workload = BASELI
 SURVEY.md R4 forces: the shipped noise_dimension=196608 needs 309 G parameters per block and cannot be
 instantiated anywhere, so noise_dimension is a flag (default 784 samples -> 2 MDCT frames -> D=1024, the
 geometry of the one runnable config); every other hyper-parameter is the config's.  The per-GPU batch is
-a flag too: the config's batch_size=128 is launch/optimizer-bound on a B200, so the default is 18944 (one
-128-row GEMM tile per SM and wave) and the config-faithful 128 is reported next to it under "sweep".
+a flag too: the config's batch_size=128 is launch/optimizer-bound on a B200, so the default is 37888 = 2 x 148 x 128
+rows: the full-batch passes run two whole waves of 128-row GEMM tiles per SM and the half-batch passes (the rows with
+r != t, data_proportion = 0.5) exactly one.  The config-faithful 128 and 18944 are reported next to it under "sweep".
 
 Keys beyond the base contract: "roofline" (tcgen05 GEMM family, per-launch CUDA events), "cpu_baseline"
 (oracle port on the host cores), "e2e" (host buffers through the public Python API), "clocks", "codec"
@@ -356,7 +357,7 @@ def run_mfac(args):
             r = timed(b, ks, max(3, args.warmup))
             sweep[f"per_gpu_batch_{b}"] = {"samples_per_s": b * ks / (r["ms_total"] * 1e-3), "ms_per_step": r["ms_per_step"],
                                            "gpu_launches": r["launches"],
-                                           "tensor_frac_whole_step": flops_per_sample(D) * b / (r["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"]}
+                                           "tensor_frac_whole_step_reference_flops": flops_per_sample(D) * b / (r["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_sustained"]}
             del r
             torch.cuda.empty_cache()
             if b <= 1024:   # launch-bound sizes: the same step replayed as one CUDA graph
@@ -484,9 +485,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mfac", choices=["mfac", "reference"])
-    ap.add_argument("--batch", type=int, default=18944, help="per-GPU batch (148 SMs x 128-row tiles)")
+    ap.add_argument("--batch", type=int, default=37888, help="per-GPU batch (2 x 148 SMs x 128-row tiles)")
     ap.add_argument("--noise-dimension", type=int, default=784, help="raw samples per example (T)")
-    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 4096])
+    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 4096, 18944])
     ap.add_argument("--quick", action="store_true", help="skip sweep / codec / cpu baseline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mfac":

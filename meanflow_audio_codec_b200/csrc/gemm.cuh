@@ -449,10 +449,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // epilogue drops from tiles * splits to about pairs + tiles.
 struct Seg { int tile, kb0, kb1; };
 struct SegIter {
-  int item, stride, num_items, splits, kbps, kbt;   // uniform
-  int g, g_end;                                     // stream-K
-  __device__ __forceinline__ SegIter(const GemmShape& sh, int tiles, int kbt_, int pair, int npairs)
-      : item(pair), stride(npairs), num_items(tiles * sh.splits), splits(sh.splits), kbps(sh.kb_per_split), kbt(kbt_), g(0), g_end(0) {
+  int item, stride, num_items, splits, kbps, kbt, tiles;   // uniform
+  int g, g_end;                                            // stream-K
+  __device__ __forceinline__ SegIter(const GemmShape& sh, int tiles_, int kbt_, int pair, int npairs)
+      : item(pair), stride(npairs), num_items(tiles_ * sh.splits), splits(sh.splits), kbps(sh.kb_per_split), kbt(kbt_),
+        tiles(tiles_), g(0), g_end(0) {
     if (splits == 0) {
       const int total = tiles * kbt, q = (total + npairs - 1) / npairs;
       g = pair * q < total ? pair * q : total;
@@ -469,14 +470,18 @@ struct SegIter {
       return true;
     }
     if (item >= num_items) return false;
-    o.tile = item / splits;
-    o.kb0 = (item - o.tile * splits) * kbps;
+    // k-slice major: the pairs of one wave work on the SAME k-slice of all the tiles, so every operand panel of that
+    // slice is fetched from HBM once and shared through L2 by the tiles of its row / column (tile-major order re-read the
+    // B panels once per tile row: 494 MB of DRAM traffic for 200 MB of operands at 37888 rows)
+    const int sp = item / tiles;
+    o.tile = item - sp * tiles;
+    o.kb0 = sp * kbps;
     o.kb1 = o.kb0 + kbps < kbt ? o.kb0 + kbps : kbt;
     item += stride;
     return true;
   }
   // tile of the segment after the current one, or -1 (uniform mode only: the look-ahead drives the L2 operand prefetch)
-  __device__ __forceinline__ int peek_tile() const { return (splits != 0 && item < num_items) ? item / splits : -1; }
+  __device__ __forceinline__ int peek_tile() const { return (splits != 0 && item < num_items) ? item % tiles : -1; }
 };
 
 constexpr int GEMM2_BN = 256;
@@ -818,12 +823,13 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
   int items = tiles * splits;
   const double uniform_waves = (double)items / pairs;
   if (split_k && stream_k_enabled() && (int64_t)tiles * k_blocks >= 8 * (int64_t)pairs &&
-      uniform_waves / std::ceil(uniform_waves) < 0.97) {
+      uniform_waves / std::ceil(uniform_waves) < 0.97 && kbps < 32) {
     // stream-K (see SegIter): every pair gets the same number of k-blocks.  Only where the best uniform slicing leaves a
     // ragged last wave: concurrent uniform items walk the same k-slice of neighbouring tiles and share those operand
     // panels in L2, stream-K ranges do not (measured at 18944 rows: 1280x1024 47 us uniform / 57 us stream-K,
     // 1280x1280 76 us uniform (4.73 waves) / 64 us stream-K).  Below ~8 k-blocks per pair the ranges are too short to pay
-    // (1024 rows: 2.42 ms/step uniform, 2.59 stream-K; 2048 rows: 2.95 / 2.84).
+    // (1024 rows: 2.42 ms/step uniform, 2.59 stream-K; 2048 rows: 2.95 / 2.84); with long uniform slices (>= 32 k-blocks,
+    // 37888 rows) the k-slice-major uniform order wins again (14.5 vs 14.7 ms/step): its waves share operand panels in L2.
     splits = 0;
     kbps = 0;
     items = pairs;

@@ -258,7 +258,7 @@ def test_reference_property_jvp_equals_reverse_mode(cuda):
     assert abs(got - directional) <= TOL * scale, (got, directional, scale)
 
 
-@pytest.mark.parametrize("B", [4096, 18944])
+@pytest.mark.parametrize("B", [4096, 18944, 37888])
 def test_full_size_step_properties(cuda, B):
     """BASELINE sizes (D=1024, L=256, C=128, 8 blocks) where the oracle is too slow: size-independent properties.
     (1) rows are independent: the first 128 rows of the big batch give the same per-example ||delta||^2, u and du/dt as a
