@@ -137,9 +137,10 @@ typedef struct MfacImfConfig {
   int32_t uniform_time;                /* 1: t ~ U(0,1) (UniformTimeSampling) instead of logit-normal, internal RNG only */
   int64_t rows_r_equals_t;             /* improved mean flow with explicit (t, r): the caller guarantees r[b] == t[b] for
                                           b < this many leading rows (sample_tr's rule, utils.py:41-44).  On those rows the
-                                          u evaluation f(z, [t, t-r]) IS the v evaluation f(z, [t, 0]), so one saved primal
-                                          pass serves both (bit-identical results, half a forward pass less at
-                                          data_proportion 0.5).  0 = no promise.  With the internal RNG the library applies
+                                          u evaluation f(z, [t, t-r]) IS the v evaluation f(z, [t, 0]) and du/dt only meets
+                                          the factor (t - r) == 0, so one saved primal pass serves both and no tangent is
+                                          computed for them (bit-identical loss and gradients; du/dt of those rows is
+                                          reported as 0).  0 = no promise.  With the internal RNG the library applies
                                           the rule itself (int(B * data_proportion) rows); -1 switches the sharing off. */
 } MfacImfConfig;
 

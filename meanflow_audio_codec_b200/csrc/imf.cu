@@ -7,9 +7,10 @@
 //
 // Every matrix product is a launch of the tcgen05 GEMM in gemm.cuh with a fused epilogue from
 // imf_kernels.cuh; the remaining work is the row kernels there.  The three network evaluations
-// of the iMF loss run as:  v-pass (B rows)  ->  u-pass primal (saves activations) interleaved with
-// the tangent pass block by block (the JVP shares W1c/W2c/W1/W2 with the primal)  ->  loss  ->
-// backward through the primal u rows and the encoder only (v and du/dt carry no gradient).
+// of the iMF loss run as:  v-pass (B rows; with the r == t rule known it is the SAVED primal pass and
+// already the u pass of those rows)  ->  u-pass primal interleaved with the tangent pass block by block
+// (the JVP shares W1c/W2c/W1/W2 with the primal; only the rows with r != t)  ->  loss  ->  backward
+// through the primal u rows and the encoder only (v and du/dt carry no gradient).
 #include "gemm.cuh"
 #include "imf_kernels.cuh"
 
