@@ -451,3 +451,25 @@ def test_stream_k_weight_gradients_match_uniform_split_k(cuda, B):
         n = shp[0] * shp[1]
         a, b = g1.flat[off:off + n], g0[off:off + n]
         assert float((a - b).norm() / b.norm()) < 1e-5, path
+
+
+@pytest.mark.parametrize("dp", [0.25, 0.3, 1.0])
+def test_shared_pass_other_data_proportions(cuda, dp):
+    """data_proportion 0.25 (a quarter of the rows shared), 0.3 (row split inside a GEMM tile) and 1.0 (every row has
+    r == t: no u pass and no tangent at all) against the plain schedule, bit for bit, on the library's own draws."""
+    import meanflow_audio_codec_b200 as m
+    D, L, C, nb, B = 128, 64, 32, 2, 300
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=model.init(2)["params"], tx=m.adamw(1e-4, 1e-4))
+    strat = m.ImprovedMeanFlowLoss(time_sampling=m.MeanFlowTimeSampling(-0.4, 1.0, dp))
+    x = 2 * torch.rand(B, D, device="cuda") - 1
+    l0, g0, a0 = strat.compute_loss(state, 4, x, return_aux=True, rows_r_equals_t=-1)
+    g0 = g0.flat.clone()
+    l1, g1, a1 = strat.compute_loss(state, 4, x, return_aux=True)
+    hrows = int(B * dp)
+    assert torch.equal(a0["t"][:hrows], a0["r"][:hrows])
+    for k in ("e", "t", "r", "v", "u", "per_example"):
+        assert torch.equal(a0[k], a1[k]), k
+    assert torch.equal(a0["dudt"][hrows:], a1["dudt"][hrows:]) and not a1["dudt"][:hrows].any()
+    assert float(l0) == float(l1) and torch.isfinite(l1)
+    assert float((g1.flat - g0).norm() / g0.norm()) < 1e-5
