@@ -76,6 +76,7 @@ struct EpiBiasGelu {
   __nv_bfloat16* g;         // [M, ld]
   __nv_bfloat16* a_out;     // [M, ld] or null
   int64_t ld;
+  int keep_rows = 0x7fffffff;   // a_out is only wanted for rows < keep_rows (the shared r == t pass: later rows get theirs from the u pass)
   using Regs = NoRegs;
   using ColRegs = BiasCol;
   __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
@@ -84,7 +85,7 @@ struct EpiBiasGelu {
   __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs& c) const {
     acc = add4(acc, c.b);
     const int64_t at = (int64_t)row * ld + col;
-    if (a_out) st_bf4(a_out + at, acc);
+    if (a_out && row < keep_rows) st_bf4(a_out + at, acc);
     st_bf4(g + at, gelu_fast4(acc));
   }
 };
@@ -216,6 +217,7 @@ struct EpiBlockOut {
   int64_t ldm, ldx;
   int s2_off;
   float inv_nb;
+  int keep_rows = 0x7fffffff;   // o_out is only wanted for rows < keep_rows
   struct Regs { uint2 s2; float4 xo; };
   using ColRegs = BiasCol;
   __device__ __forceinline__ void prefetch(int m0, int n0, int bn, int M, int N, int etid) const {
@@ -232,7 +234,7 @@ struct EpiBlockOut {
     const int64_t at = (int64_t)row * ldx + col;
     const float4 s2 = bf4_to_f4(r.s2), xo = r.xo;
     acc = add4(acc, c.b);
-    if (o_out) st_bf4(o_out + at, acc);
+    if (o_out && row < keep_rows) st_bf4(o_out + at, acc);
     st_f4(x_new + at, make_float4(acc.x * ((1.0f + s2.x) * inv_nb) + xo.x, acc.y * ((1.0f + s2.y) * inv_nb) + xo.y,
                                   acc.z * ((1.0f + s2.z) * inv_nb) + xo.z, acc.w * ((1.0f + s2.w) * inv_nb) + xo.w));
   }

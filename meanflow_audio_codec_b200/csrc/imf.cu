@@ -390,16 +390,17 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     SavedBlock& sb = p.blk[k];
     return gemm_linear_bf16(sb.gc + r0 * d.Ca, d.Ca, w + d.s_c2w, rows, d.Mp, d.Cp, bias + d.b_c2, sb.m + r0 * d.Mp, d.Mp, s);
   };
-  auto primal_mlp = [&](int k, int64_t r0, int rows) -> int {
+  // keep: rows (relative to r0) whose pre-activation a and block output o are stored for the tangent pass / backward
+  auto primal_mlp = [&](int k, int64_t r0, int rows, int keep) -> int {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
     SavedBlock& sb = p.blk[k];
     float* x_in = p.xs + (int64_t)k * B * d.Dp + r0 * d.Dp;
     float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp + r0 * d.Dp;
-    MFAC_OK(gemm_bias_gelu(sb.hin + r0 * d.Ip, d.Ip, w + d.s_m1w, rows, d.Ip, d.Ip, bias + d.b_m1, sb.g + r0 * d.Ip,
-                           sb.a + r0 * d.Ip, d.Ip, s));
+    MFAC_OK(gemm_fwd(sb.hin + r0 * d.Ip, d.Ip, w + d.s_m1w, rows, d.Ip, d.Ip,
+                     EpiBiasGelu{bias + d.b_m1, sb.g + r0 * d.Ip, sb.a + r0 * d.Ip, d.Ip, keep}, s));
     return gemm_fwd(sb.g + r0 * d.Ip, d.Ip, w + d.s_m2w, rows, d.Dp, d.Ip,
-                    EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb}, s);
+                    EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb, keep}, s);
   };
   // ---- v = f(z, [t, 0], lat)
   if (share) {
@@ -411,7 +412,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
       MFAC_OK(primal_mod(k, 0, M));
       LnModArgs la{p.lat, p.xs + (int64_t)k * B * d.Dp, sb.m, sb.hin, nullptr, nullptr, nullptr, sb.mu, sb.rstd, d.Mp};
       MFAC_OK(lnmod(false, la, d, B, s));
-      MFAC_OK(primal_mlp(k, 0, M));
+      MFAC_OK(primal_mlp(k, 0, M, (int)h));   // rows [h, B) get their a / o from the u pass below
     }
     // v is the tangent seed of the rows that still get a u pass (and an optional test output for all rows)
     const int64_t v0 = (aux && aux->v) ? 0 : h;
@@ -446,7 +447,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
                  sb.mu + h, sb.rstd + h, d.Mp};
     MFAC_OK(lnmod(tangent, la, d, Mu, s));
     // the tangent GEMMs read the primal pre-activation a and block output o: primal first
-    MFAC_OK(primal_mlp(k, h, Mu));
+    MFAC_OK(primal_mlp(k, h, Mu, Mu));
     if (tangent) {
       MFAC_OK(gemm_fwd(p.hind + h * d.Ip, d.Ip, w + d.s_m1w, Mu, d.Ip, d.Ip, EpiMulDgelu{sb.a + h * d.Ip, p.gd + h * d.Ip, d.Ip}, s));
       MFAC_OK(gemm_fwd(p.gd + h * d.Ip, d.Ip, w + d.s_m2w, Mu, d.Dp, d.Ip,
