@@ -212,3 +212,23 @@ def test_mean_flow_clips_t_minus_r_and_weights():
         dsq = (a["delta"] ** 2).mean(-1)
         np.testing.assert_allclose(a["weights"], (dsq + 1e-3) ** (gamma - 1.0), rtol=1e-12)
         assert abs(a["loss"] - (a["weights"] * dsq).mean()) < 1e-14
+
+
+def test_utils_mirror_matches_the_oracle_definitions():
+    """utils.py:5-45 helper functions of the host mirror against the oracle's restatements."""
+    from meanflow_audio_codec_b200 import utils as U
+    x = torch.linspace(0, 1, 7)
+    np.testing.assert_allclose(U.sinusoidal_embedding(x, 32).numpy(), imf_np.sinusoidal_embedding(x.numpy().astype(np.float64), 32)[0],
+                               atol=2e-6)
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((5, 11)), rng.standard_normal((5, 11))
+    want, _, _ = imf_np.weighted_l2(a - b)
+    got = U.weighted_l2_loss(torch.from_numpy(a), torch.from_numpy(b))
+    assert abs(float(got) - want) < 1e-12
+    t, r = U.sample_tr(3, 64)
+    assert t.shape == r.shape == (64, 1) and bool((r <= t).all()) and bool((r[:32] == t[:32]).all()) and bool((r[32:] < t[32:]).any())
+    t2, r2 = U.sample_tr(3, 64)
+    assert torch.equal(t, t2) and torch.equal(r, r2)
+    assert U.ema(None, 2.0) == 2.0 and abs(U.ema(1.0, 2.0, beta=0.9) - 1.1) < 1e-12
+    ln = U.logit_normal(0, (10000, 1))
+    assert 0.40 < float(ln.mean()) < 0.44
