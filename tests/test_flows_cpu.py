@@ -98,3 +98,63 @@ def test_oracle_block_properties():
     gx = np.sqrt((v * v).sum(axis=(1, 2)))
     np.testing.assert_allclose(g, v * (gx / (gx.mean(-1, keepdims=True) + 1e-6))[:, None, None, :], rtol=1e-12)
     assert math.isfinite(float(np.abs(g).max()))
+
+
+def _np_tree(t):
+    return {k: (_np_tree(v) if isinstance(v, dict) else v.numpy().astype(np.float64)) for k, v in t.items()}
+
+
+def _t64(t):
+    return {k: (_t64(v) if isinstance(v, dict) else v.double()) for k, v in t.items()}
+
+
+@pytest.mark.parametrize("arch", ["mlp_mixer", "convnet"])
+def test_torch_restatement_matches_numpy_and_supports_the_loss_strategies(arch):
+    """oracle/flows_torch.py (the oracle of the next scope row): forward equals the NumPy restatement; the
+    three loss strategies run through autograd + jvp around it with an MLPEncoder, and keep the reference's two iMF
+    properties (test/test_improved_mean_flow.py:31-100): r == t gives v_pred == u, forward-mode du/dt equals reverse mode."""
+    from oracle import flows_torch as ft
+    D, Cd, nb, L, B = 64, 32, 2, 8, 4
+    gen = torch.Generator().manual_seed(0)
+    if arch == "mlp_mixer":
+        model = m.ConditionalMLPMixerFlow(D, Cd, nb, latent_dimension=L, token_mix_dim=32, channel_mix_dim=24, num_channels=16,
+                                          num_latent_tokens=1)
+        kw = dict(num_blocks=nb, num_channels=16, condition_dimension=Cd)
+        fnp, fto = flows_np.mixer_forward, ft.mixer_forward
+    else:
+        model = m.ConditionalConvFlow(D, Cd, nb, latent_dimension=L, num_latent_tokens=1)
+        kw = dict(num_blocks=nb, condition_dimension=Cd)
+        fnp, fto = flows_np.conv_forward, ft.conv_forward
+    p = model.init(1, device="cpu")["params"]
+    p64 = _t64(p)
+    ft.map_tree(lambda v: v.add_(0.05 * torch.randn(v.shape, generator=gen, dtype=torch.float64)), p64)   # biases, GRN, layer scale
+    x = torch.randn(B, D, generator=gen, dtype=torch.float64)
+    e = torch.randn(B, D, generator=gen, dtype=torch.float64)
+    time = torch.rand(B, 2, generator=gen, dtype=torch.float64)
+    lat = torch.randn(B, 1, L, generator=gen, dtype=torch.float64)
+    want = fnp(_np_tree(p64), x.numpy(), time.numpy(), lat.numpy(), **kw)
+    got = fto(p64, x, time, lat, **kw)
+    np.testing.assert_allclose(got.numpy(), want, atol=1e-10)
+    fwd = lambda pp, z, tm, la: fto(pp, z, tm, la, **kw)  # noqa: E731
+    pe = {"dense1": {"kernel": torch.randn(D, 16, generator=gen, dtype=torch.float64) / 8, "bias": torch.zeros(16, dtype=torch.float64)},
+          "dense2": {"kernel": torch.randn(16, L, generator=gen, dtype=torch.float64) / 4, "bias": torch.zeros(L, dtype=torch.float64)}}
+    t = torch.rand(B, 1, generator=gen, dtype=torch.float64)
+    r = t * torch.rand(B, 1, generator=gen, dtype=torch.float64)
+    for method in ("improved_mean_flow", "mean_flow", "flow_matching"):
+        loss, gp, gpe, aux = ft.strategy_loss_and_grads(fwd, p64, pe, x, e, t, r, method=method)
+        assert torch.isfinite(loss)
+        assert all(torch.isfinite(v).all() for b in gpe.values() for v in b.values())
+        assert float(gpe["dense1"]["kernel"].abs().sum()) > 0          # the encoder is trained through latent_proj
+    # r == t: v_pred == u  (the (t - r) factor is exactly 0)
+    loss_a, _, _, aux = ft.strategy_loss_and_grads(fwd, p64, pe, x, e, t, t.clone())
+    target = 0.999 * e - x
+    s = ((aux["u"].detach() - target) ** 2).sum(-1)
+    assert abs(float(((1.0 / (s + 1e-3)) * s).mean()) - float(loss_a)) < 1e-12
+    # forward-mode du/dt == reverse-mode directional derivative
+    _, _, _, aux = ft.strategy_loss_and_grads(fwd, p64, pe, x, e, t, r)
+    lat_e = ft.mlp_encoder(pe, x)[:, None, :]
+    z = ((1 - t) * x + (0.001 + 0.999 * t) * e).requires_grad_(True)
+    tt = t.clone().requires_grad_(True)
+    out = fto(p64, z, torch.cat([tt, tt - r], -1), lat_e, **kw).sum()
+    gz, gt = torch.autograd.grad(out, (z, tt))
+    assert abs(float((gz * aux["v"].detach()).sum() + gt.sum()) - float(aux["dudt"].sum())) < 1e-8
