@@ -35,7 +35,7 @@ extern "C" {
 #define MFAC_ERR_NCCL (-6)         /* NCCL unavailable or returned an error */
 /* CUDA runtime errors are returned as -(1000 + cudaError_t). */
 
-MFAC_API int mfac_version(void);
+MFAC_API int mfac_version(void);   /* 101: MfacImfConfig gained method, gamma, uniform_time, rows_r_equals_t */
 MFAC_API const char* mfac_status_string(int status);
 
 /* ------------------------------------------------------------------ MDCT / IMDCT

@@ -105,7 +105,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t inner, int64_t out
 
 extern "C" {
 
-int mfac_version(void) { return 100; }
+int mfac_version(void) { return 101; }   // 101: MfacImfConfig gained method / gamma / uniform_time / rows_r_equals_t
 
 const char* mfac_status_string(int status) {
   switch (status) {
