@@ -307,6 +307,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (descriptor prefetch, barrier init, TMEM allocation) touched no global
+  // memory and may run under the tail of the previous kernel in the stream; let our own successor start its set-up, then
+  // wait until the predecessor has completed and its writes are visible.  (Both are no-ops for a plain launch.)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
@@ -545,6 +550,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   cluster_sync_all();                                // barriers of both CTAs initialised before any remote access
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (descriptor prefetch, barrier init, TMEM allocation) touched no global
+  // memory and may run under the tail of the previous kernel in the stream; let our own successor start its set-up, then
+  // wait until the predecessor has completed and its writes are visible.  (Both are no-ops for a plain launch.)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -717,6 +727,27 @@ void count_launch();
 void* profile_begin(int family, double work, cudaStream_t s, const char* label = nullptr, int M = 0, int N = 0, int K = 0);
 void profile_end(void* token, cudaStream_t s);
 
+// GEMM launches carry the programmatic-stream-serialization attribute: a GEMM that follows another GEMM starts its
+// set-up as soon as the predecessor's CTAs have passed theirs (MFAC_NO_PDL=1 launches plainly).
+inline bool pdl_enabled() {
+  static const bool on = getenv("MFAC_NO_PDL") == nullptr;
+  return on;
+}
+template <class Kern, class... Args>
+inline void launch_pdl(Kern kern, int grid, int threads, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N, int K, const Epi& epi,
                    cudaStream_t stream, int splits) {
@@ -760,7 +791,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
     maps.m[1] = tmA;
   }
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, maps, shape, epi);
+  launch_pdl(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, maps, shape, epi);
   profile_end(prof, stream);
   count_launch();
   return launch_status();
@@ -837,7 +868,7 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
   const int grid = 2 * (items < pairs ? items : pairs);
   GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off(), splits != 1 ? 0 : sweep_next()};
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, shape, epi);
+  launch_pdl(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, shape, epi);
   profile_end(prof, stream);
   count_launch();
   return launch_status();
