@@ -734,10 +734,10 @@ inline bool pdl_enabled() {
   return on;
 }
 template <class Kern, class... Args>
-inline void launch_pdl(Kern kern, int grid, int threads, size_t smem, cudaStream_t stream, Args... args) {
+inline void launch_pdl(Kern kern, dim3 grid, dim3 threads, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)threads);
+  cfg.gridDim = grid;
+  cfg.blockDim = threads;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -791,7 +791,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
     maps.m[1] = tmA;
   }
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
-  launch_pdl(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, maps, shape, epi);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, maps, shape, epi);
   profile_end(prof, stream);
   count_launch();
   return launch_status();
@@ -868,7 +868,7 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
   const int grid = 2 * (items < pairs ? items : pairs);
   GemmShape shape{M, N, K, splits, kbps, epi_prefetch_off(), splits != 1 ? 0 : sweep_next()};
   void* prof = profile_begin(MFAC_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream, Epi::name, M, N, K);
-  launch_pdl(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, shape, epi);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, shape, epi);
   profile_end(prof, stream);
   count_launch();
   return launch_status();

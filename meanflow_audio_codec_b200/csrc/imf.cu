@@ -85,8 +85,8 @@ int lnmod(bool tangent, const LnModArgs& a_in, const Dims& d, int64_t B, cudaStr
   const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 8), tgrid = (unsigned)ceil_div<int64_t>(B, 4);
 #define MFAC_LNMOD_CASE(NVV)                                                              \
   case NVV:                                                                               \
-    if (tangent) lnmod_vec_kernel<NVV, true><<<tgrid, 128, 0, s>>>(a, d, B);              \
-    else lnmod_vec_kernel<NVV, false><<<vgrid, 256, 0, s>>>(a, d, B);                     \
+    if (tangent) launch_pdl(lnmod_vec_kernel<NVV, true>, dim3(tgrid), dim3(128), 0, s, a, d, B);   \
+    else launch_pdl(lnmod_vec_kernel<NVV, false>, dim3(vgrid), dim3(256), 0, s, a, d, B);        \
     break;
   switch (nv) {
     MFAC_LNMOD_CASE(1) MFAC_LNMOD_CASE(2) MFAC_LNMOD_CASE(3) MFAC_LNMOD_CASE(4)
@@ -104,7 +104,7 @@ int ln_bwd(const LnBwdArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
   LnBwdArgs a = a_in;
   a.reverse = vec_rows(d) ? sweep_next() : 0;
   const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 4);   // ~200 registers per thread: 4-row CTAs, two per SM
-#define MFAC_LNBWD_CASE(NVV) case NVV: ln_bwd_vec_kernel<NVV><<<vgrid, 128, 0, s>>>(a, d, B); break;
+#define MFAC_LNBWD_CASE(NVV) case NVV: launch_pdl(ln_bwd_vec_kernel<NVV>, dim3(vgrid), dim3(128), 0, s, a, d, B); break;
   switch (vec_rows(d)) {
     MFAC_LNBWD_CASE(1) MFAC_LNBWD_CASE(2) MFAC_LNBWD_CASE(3) MFAC_LNBWD_CASE(4)
     MFAC_LNBWD_CASE(5) MFAC_LNBWD_CASE(6) MFAC_LNBWD_CASE(7) MFAC_LNBWD_CASE(8)
@@ -164,7 +164,7 @@ int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* out, int kind, int 
            int ncols = 0) {
   if (ncols == 0) ncols = ld;
   const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
-  colsum_atomic_vec_kernel<<<dim3(ceil_div(ncols, 256), R), 256, 0, s>>>(G, ld, ncols, B, out, kind, limit, d);
+  launch_pdl(colsum_atomic_vec_kernel, dim3(ceil_div(ncols, 256), R), dim3(256), 0, s, G, ld, ncols, B, out, kind, limit, d);
   count_launch();
   return launch_status();
 }
@@ -378,7 +378,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   // with e - x
   PrepArgs pa{x, e, t, r, p.e, need_v && !share ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
               p.xb, p.t, p.r, need_v ? p.cond_v : nullptr, p.cond_u, p.dcond_u, *cfg, B};
-  imf_prep_kernel<<<(unsigned)B, ROW_THREADS, 0, s>>>(pa, d);
+  launch_pdl(imf_prep_kernel, dim3((unsigned)B), dim3(ROW_THREADS), 0, s, pa, d);
   count_launch();
   // ---- latents = encode(x)
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
@@ -459,9 +459,9 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
   // ---- loss and its seed gradient
   LossArgs lo{u, tangent ? p.xd : nullptr, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};
-  imf_loss_kernel<<<(unsigned)B, ROW_THREADS, (size_t)d.Dp * 4, s>>>(lo, d);
+  launch_pdl(imf_loss_kernel, dim3((unsigned)B), dim3(ROW_THREADS), (size_t)d.Dp * 4, s, lo, d);
   count_launch();
-  sum_rows_kernel<<<1, 1024, 0, s>>>(p.row_loss, B, loss);
+  launch_pdl(sum_rows_kernel, dim3(1), dim3(1024), 0, s, (const float*)p.row_loss, B, loss);
   count_launch();
   // ---- backward through the primal u rows (weight gradients accumulate split-K partials atomically)
   MFAC_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)d.total * 4, s));
@@ -472,8 +472,9 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     float* gk = grads + (int64_t)k * d.blk_stride;
     const float* x_in = p.xs + (int64_t)k * B * d.Dp;
     // g_o, g_s2 and both of their bias-gradient column sums (db2, the s2 third of dbc2) in one pass
-    bwd_block_out_vec_kernel<<<dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), 256, 0, s>>>(
-        p.g_x, sb.m, sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B, sweep_next());
+    launch_pdl(bwd_block_out_vec_kernel, dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), dim3(256), 0, s,
+               (const float*)p.g_x, (const __nv_bfloat16*)sb.m, (const __nv_bfloat16*)sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B,
+               sweep_next());
     count_launch();
     MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
     // Unpadded geometries: the dX epilogues that write g_a and g_shift also accumulate their column sums (db1 and the shift

@@ -99,6 +99,7 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims d) {
+  MFAC_PDL_SYNC();
   const int64_t b = blockIdx.x;
   const uint64_t step = a.cfg.step_dev ? *a.cfg.step_dev : a.cfg.step;
   __shared__ float s_tr[2];
@@ -288,6 +289,7 @@ struct LossArgs {
   int64_t B;
 };
 __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims d) {
+  MFAC_PDL_SYNC();
   extern __shared__ __align__(16) float s_delta[];  // [Dp]
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
 }
 // deterministic sum of row_loss[B] -> loss
 __global__ void __launch_bounds__(1024) sum_rows_kernel(const float* v, int64_t n, float* out) {
+  MFAC_PDL_SYNC();
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -478,6 +481,7 @@ __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) 
 
 template <int NV, bool TANGENT>
 __global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_vec_kernel(LnModArgs a, Dims d, int64_t B) {
+  MFAC_PDL_SYNC();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)(a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -575,6 +579,7 @@ __global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_ve
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, int64_t B) {
+  MFAC_PDL_SYNC();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)(a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -632,6 +637,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
 __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o,
                                                                 __nv_bfloat16* g_o, __nv_bfloat16* g_m, float* db_o, float* db_m,
                                                                 Dims d, int64_t B, int reverse) {
+  MFAC_PDL_SYNC();
   __shared__ float s_red[2][8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -677,6 +683,7 @@ __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x
 // split-K weight gradients it sits next to).
 __global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloat16* G, int ld, int ncols, int64_t B, float* out,
                                                                 int kind, int limit, Dims d) {
+  MFAC_PDL_SYNC();
   __shared__ float s_red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;

@@ -30,6 +30,12 @@
     if (_s != MFAC_SUCCESS) return _s; \
   } while (0)
 
+// Device side of a kernel that takes part in the chain: let the successor start its set-up, then wait for the predecessor
+// (first statements of the kernel, before any global access; no-ops under a plain launch).
+#define MFAC_PDL_SYNC()                                   \
+  asm volatile("griddepcontrol.launch_dependents;");      \
+  asm volatile("griddepcontrol.wait;" ::: "memory")
+
 namespace mfac {
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? MFAC_SUCCESS : -(1000 + (int)e); }
