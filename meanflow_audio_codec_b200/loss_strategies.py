@@ -14,7 +14,7 @@ from abc import ABC, abstractmethod
 import torch
 
 from . import _lib
-from .mlp_flow import ConditionalFlow, ParamTree, TrainState
+from .mlp_flow import ConditionalFlow, TrainState
 
 
 class LinearNoiseSchedule:

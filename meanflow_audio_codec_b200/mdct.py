@@ -14,7 +14,6 @@ direct-cosine definition, which is what the reference's test pins.
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass
 
 import torch
