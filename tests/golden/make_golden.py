@@ -45,5 +45,17 @@ def main():
     print("wrote", OUT / "mdct_reference_baseline.npz", sum(v.nbytes for v in blob.values()) / 1e6, "MB raw")
 
 
+def copy_reference_config():
+    """tests/golden/config_imf_mlp_mnist_mdct.json is BASELINE.json configs[0] as the reference ships it
+    (configs/method=improved_mean_flow--architecture=mlp--dataset=mnist--tokenization=mdct.json): a data fixture in the
+    reference's own file format, used by the drop-in tests (tests/test_abi_cpu.py, tests/test_imf_gpu.py)."""
+    import json
+    src = Path("/root/reference/configs/method=improved_mean_flow--architecture=mlp--dataset=mnist--tokenization=mdct.json")
+    dst = Path(__file__).resolve().parent / "config_imf_mlp_mnist_mdct.json"
+    dst.write_text(json.dumps(json.loads(src.read_text()), indent=2, sort_keys=True) + "\n")
+
+
 if __name__ == "__main__":
     main()
+    copy_reference_config()
+

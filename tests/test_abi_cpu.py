@@ -165,3 +165,22 @@ def test_create_loss_strategy_follows_the_reference_factory():
     assert t.shape == (1000, 1) and 0.38 < float(t.mean()) < 0.46
     u = m.UniformTimeSampling().sample_time(0, 1000, device="cpu")
     assert u.shape == (1000, 1) and 0.45 < float(u.mean()) < 0.55
+
+
+def test_reference_config_file_drives_the_factories():
+    """BASELINE.json configs[0] in the reference's own file format (tests/golden/config_imf_mlp_mnist_mdct.json, copied by
+    tests/golden/make_golden.py) through the three factories the reference's train_flow uses (trainers/train.py:178-264)."""
+    from meanflow_audio_codec_b200.config import load_config
+    cfg = load_config(ROOT / "tests" / "golden" / "config_imf_mlp_mnist_mdct.json")
+    assert cfg.batch_size == 128 and cfg.loss_strategy is None and cfg.time_sampling is None
+    tok = m.create_tokenization_strategy(cfg)
+    assert (tok.config.window_size, tok.config.hop_size) == (512, 256)
+    D = m.compute_tokenized_dimension(tok, cfg.noise_dimension, cfg.dataset)
+    assert D == 1024 and m.compute_token_shape(tok, cfg.noise_dimension, cfg.dataset) == (2, 512)
+    model = m.create_flow_model(load_config({**cfg.to_dict(), "noise_dimension": D}))
+    assert isinstance(model, m.ConditionalFlow) and model.param_count() == 28_262_272   # SURVEY 8a: 28.26 M
+    strat = m.create_loss_strategy(cfg)
+    assert isinstance(strat, m.ImprovedMeanFlowLoss) and strat.use_weighted_loss and strat.c == 1e-3
+    assert (strat.time_sampling.mean, strat.time_sampling.std, strat.time_sampling.data_proportion) == (-0.4, 1.0, 0.5)
+    opt = m.adamw(cfg.base_lr, cfg.weight_decay)
+    assert (opt.learning_rate, opt.weight_decay, opt.b1, opt.b2, opt.eps) == (1e-4, 1e-4, 0.9, 0.999, 1e-8)

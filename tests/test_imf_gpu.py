@@ -473,3 +473,35 @@ def test_shared_pass_other_data_proportions(cuda, dp):
     assert torch.equal(a0["dudt"][hrows:], a1["dudt"][hrows:]) and not a1["dudt"][:hrows].any()
     assert float(l0) == float(l1) and torch.isfinite(l1)
     assert float((g1.flat - g0).norm() / g0.norm()) < 1e-5
+
+
+def test_reference_training_loop_drops_in(cuda, tmp_path):
+    """The reference's train_flow loop (trainers/train.py:178-264, 323-347, 364-387, 406-408) written against this package,
+    driven by BASELINE.json configs[0] in the reference's own config-file format: tokenise -> train_step -> checkpoint ->
+    sample -> detokenise.  (The full-size model of the config; three steps on synthetic data in [-1, 1].)"""
+    from pathlib import Path
+    import meanflow_audio_codec_b200 as m
+    from meanflow_audio_codec_b200 import checkpoint as ck
+    from meanflow_audio_codec_b200.config import load_config
+    cfg = load_config(Path(__file__).resolve().parent / "golden" / "config_imf_mlp_mnist_mdct.json")
+    tok = m.create_tokenization_strategy(cfg)                                          # train.py:178
+    D = m.compute_tokenized_dimension(tok, cfg.noise_dimension, cfg.dataset)
+    model = m.create_flow_model(load_config({**cfg.to_dict(), "noise_dimension": D}))
+    state = m.TrainState.create(apply_fn=model.apply, params=model.init(cfg.seed)["params"],
+                                tx=m.adamw(cfg.base_lr, cfg.weight_decay))             # train.py:236-264
+    strat = m.create_loss_strategy(cfg)                                                # train.py:52-153
+    g = torch.Generator(device="cuda").manual_seed(cfg.seed)
+    key, losses = cfg.seed, []
+    for step in range(3):
+        batch = 2 * torch.rand(cfg.batch_size, cfg.noise_dimension, device="cuda", generator=g) - 1
+        x = tok.tokenize(batch).reshape(cfg.batch_size, -1)                            # train.py:339-341
+        state, loss, key = m.train_step(state, key, x, strat)                          # train.py:345
+        losses.append(float(loss))
+    assert state.step == 3 and all(np.isfinite(losses)) and all(0.9 < v <= 1.0 for v in losses)   # SURVEY R9: saturates near 1
+    path = tmp_path / "checkpoints" / f"step_{state.step:05d}.msgpack"                # train.py:406-408
+    ck.save_checkpoint(path, state)
+    assert ck.get_checkpoint_step(path) == 3 and path.stat().st_size > 3 * 4 * model.param_count()
+    lat = model.apply({"params": state.params}, x, method="encode")
+    smp = m.sample(state.apply_fn, D, state.params, cfg.sample_seed, latents=lat, n_steps=2)    # train.py:371-380
+    audio = tok.detokenize(smp.reshape(cfg.batch_size, -1, tok.config.window_size))             # train.py:387
+    assert audio.shape == (cfg.batch_size, 1280) and torch.isfinite(audio).all()
