@@ -344,10 +344,10 @@ int conv_forward_impl(const MfacConvDims& d, const MfacConvWeights& w, const flo
   const int SC = d.S * d.S * CH;
   const size_t smem = convnext_smem<CH>(d.S);
   if (smem > 227 * 1024) return MFAC_ERR_UNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     MFAC_CUDA_OK(cudaFuncSetAttribute(convnext_block_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    configured.done();
   }
   copy_pair_kernel<<<nblk(B * d.D, 256), 256, 0, s>>>(x, p.x, p.xb, B * d.D);
   count_launch();
@@ -404,6 +404,7 @@ int mfac_mixer_forward(const MfacMixerDims* d, const MfacMixerWeights* w, const 
   p.plan(ar, *d, B);
   if (ar.overflow) return MFAC_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  sweep_reset();
   switch (d->channels) {
     case 8: return mixer_forward_impl<8>(*d, *w, x, time, latents, out, B, p, s);
     case 16: return mixer_forward_impl<16>(*d, *w, x, time, latents, out, B, p, s);
@@ -432,6 +433,7 @@ int mfac_conv_forward(const MfacConvDims* d, const MfacConvWeights* w, const flo
   p.plan(ar, *d, B);
   if (ar.overflow) return MFAC_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  sweep_reset();
   switch (d->channels) {
     case 4: return conv_forward_impl<4>(*d, *w, x, time, latents, out, B, p, s);
     case 8: return conv_forward_impl<8>(*d, *w, x, time, latents, out, B, p, s);

@@ -84,12 +84,17 @@ struct GemmShape {
 // kernels of a chain alternate between ascending and descending rows, so that each one starts on the rows its producer
 // touched last -- the part of the producer's output that is still in the 126 MB L2 (the step's tensors are 40-270 MB each).
 // Results do not depend on the direction.  MFAC_NO_SWEEP_ALTERNATE=1 keeps every kernel ascending.
+// The direction state is per calling thread and is reset by every C-ABI entry point (sweep_reset), so the traversal order
+// of a call's kernels depends on that call alone, never on what the thread launched before.
+inline int& sweep_state() {
+  static thread_local int cur = 0;
+  return cur;
+}
+inline void sweep_reset() { sweep_state() = 0; }
 inline int sweep_next() {
   static const int on = getenv("MFAC_NO_SWEEP_ALTERNATE") ? 0 : 1;
-  static thread_local int cur = 0;
   if (!on) return 0;
-  cur ^= 1;
-  return cur;
+  return sweep_state() ^= 1;
 }
 // The L2 prefetch of the next tile's epilogue operands paid while the epilogues were latency-bound; with the current
 // register prefetch it only adds DRAM traffic (lines fetched early are evicted before use: 371 MB read against 294 MB of
@@ -766,13 +771,13 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   // FULL: every tile lies inside the matrix, so the epilogue carries no row / column predicates (and half the code).
   const bool full = (M % GEMM_BM == 0) && (N % BN == 0);
   auto kern = full ? gemm_tcgen05_kernel<BN, A_MN, B_MN, true, Epi> : gemm_tcgen05_kernel<BN, A_MN, B_MN, false, Epi>;
-  static bool configured = false;  // one per template instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // one per template instantiation
+  if (configured.need()) {
     MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, true, Epi>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, false, Epi>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured.done();
   }
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int k_blocks = ceil_div(K, GEMM_BK);
@@ -827,13 +832,13 @@ int launch_gemm_pair(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, 
   }
   const bool full = (M % (2 * GEMM_BM) == 0) && (N % GEMM2_BN == 0);
   auto kern = full ? gemm_tcgen05_pair_kernel<A_MN, B_MN, true, Epi> : gemm_tcgen05_pair_kernel<A_MN, B_MN, false, Epi>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<A_MN, B_MN, true, Epi>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     MFAC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<A_MN, B_MN, false, Epi>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured.done();
   }
   const int tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, GEMM2_BN);
   const int k_blocks = ceil_div(K, GEMM_BK);

@@ -72,13 +72,13 @@ int lnmod(bool tangent, const LnModArgs& a_in, const Dims& d, int64_t B, cudaStr
   a.reverse = vec_rows(d) ? sweep_next() : 0;
   const size_t smem = (size_t)d.Ip * 4 * (tangent ? 2 : 1);
   if (smem > 200 * 1024) return MFAC_ERR_UNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     MFAC_CUDA_OK(cudaFuncSetAttribute(lnmod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MFAC_CUDA_OK(cudaFuncSetAttribute(lnmod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MFAC_CUDA_OK(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MFAC_CUDA_OK(cudaFuncSetAttribute(imf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured.done();
   }
   const int nv = vec_rows(d);
   // the tangent variant keeps a whole row's operands in flight (~250 registers): 4-row CTAs so that two fit an SM
@@ -293,6 +293,7 @@ size_t mfac_workspace_bytes(int32_t kind, const MfacMlpDims* dims, int64_t B) {
 int mfac_mlp_encode(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x, float* latents,
                     int64_t B, void* ws, size_t ws_bytes, void* stream) {
   (void)params;
+  sweep_reset();
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!shadow || !x || !latents) return MFAC_ERR_NULL;
@@ -315,6 +316,7 @@ int mfac_mlp_encode(const MfacMlpDims* dims, const float* params, const void* sh
 int mfac_mlp_forward(const MfacMlpDims* dims, const float* params, const void* shadow, const float* x, const float* time,
                      const float* latents, float* out, int64_t B, void* ws, size_t ws_bytes, void* stream) {
   (void)params;
+  sweep_reset();
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!shadow || !x || !time || !out) return MFAC_ERR_NULL;
@@ -344,6 +346,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
                        const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
                        const MfacImfAux* aux, int64_t B, void* ws, size_t ws_bytes, void* stream) {
   (void)params;
+  sweep_reset();
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!cfg || !shadow || !x || !loss || !grads) return MFAC_ERR_NULL;
@@ -540,6 +543,7 @@ int mfac_sample(const MfacMlpDims* dims, const float* params, const void* shadow
                 int32_t mode, int32_t n_steps, float guidance_scale, uint64_t seed, float* out, int64_t B, void* ws,
                 size_t ws_bytes, void* stream) {
   (void)params;
+  sweep_reset();
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!shadow || !latents || !out) return MFAC_ERR_NULL;

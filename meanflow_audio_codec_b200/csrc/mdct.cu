@@ -891,10 +891,10 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
   if (N == FFT_N && hop == FFT_H && io.in_elem_stride == 1 && io.out_elem_stride == FFT_N &&
       (io.out_clip_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 7) == 0) {
     MFAC_OK(get_tables(N, true, &ts));
-    static bool configured2 = false;
-    if (!configured2) {
+    static PerDeviceOnce configured2;
+    if (configured2.need()) {
       MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-      configured2 = true;
+      configured2.done();
     }
     void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)B * ((double)T + (double)nf * N), stream);
     if (nf <= F2_FRAMES / 2) {
@@ -902,10 +902,10 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
       const int cpc = F2_FRAMES / (int)nf;
       const int need = ((int)nf - 1) * FFT_H + 2 * FFT_N;
       const size_t smem_s = (size_t)2 * cpc * (need / 2 / 128 * 144) * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
-      static bool configured3 = false;
-      if (!configured3) {
+      static PerDeviceOnce configured3;
+      if (configured3.need()) {
         MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512h256_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured3 = true;
+        configured3.done();
       }
       mdct512h256_short_kernel<<<(unsigned)ceil_div<int64_t>(B, cpc), F2_THREADS, smem_s, stream>>>(
           x, X, ts.fft, T, (int)nf, cpc, B, io.in_clip_stride, io.out_clip_stride);
@@ -920,10 +920,10 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
   if (N == FFT_N && seg_len <= 40960) {
     MFAC_OK(get_tables(N, true, &ts));
     const size_t smem = TABLE_BYTES + SCRATCH_BYTES + (size_t)seg_len * 4;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
       MFAC_CUDA_OK(cudaFuncSetAttribute(mdct512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+      configured.done();
     }
     dim3 grid((unsigned)ceil_div<int64_t>(nf, fpc), (unsigned)B);
     void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)B * ((double)T + (double)nf * N), stream);
@@ -935,10 +935,10 @@ int mdct_forward(const float* x, float* X, StridedIO io, int64_t B, int64_t T, i
   if (N > 4096) return MFAC_ERR_UNSUPPORTED;
   MFAC_OK(get_tables(N, false, &ts));
   const size_t smem = (size_t)DENSE_FR * 2 * N * 4;
-  static bool configured_dense = false;
-  if (!configured_dense) {
+  static PerDeviceOnce configured_dense;
+  if (configured_dense.need()) {
     MFAC_CUDA_OK(cudaFuncSetAttribute(mdct_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured_dense = true;
+    configured_dense.done();
   }
   const int64_t fy = ceil_div<int64_t>(nf, DENSE_FR);
   if (fy > 65535) return MFAC_ERR_UNSUPPORTED;
@@ -963,10 +963,10 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
   if (N == FFT_N && hop == FFT_H && io.out_elem_stride == 1 && io.in_elem_stride == FFT_N &&
       (io.in_clip_stride % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 7) == 0) {
     MFAC_OK(get_tables(N, true, &ts));
-    static bool configured2 = false;
-    if (!configured2) {
+    static PerDeviceOnce configured2;
+    if (configured2.need()) {
       MFAC_CUDA_OK(cudaFuncSetAttribute(imdct512h256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM));
-      configured2 = true;
+      configured2.done();
     }
     void* prof = profile_begin(MFAC_PROF_IMDCT, 4.0 * (double)B * ((double)L + (double)nf * N), stream);
     const int64_t nblocks = nf + 3;
@@ -997,10 +997,10 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
   }
   if (N == FFT_N && smem <= 160 * 1024) {  // tiny hops (< ~16) fall through to the dense path
     MFAC_OK(get_tables(N, true, &ts));
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
       MFAC_CUDA_OK(cudaFuncSetAttribute(imdct512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+      configured.done();
     }
     dim3 grid((unsigned)ceil_div<int64_t>(L, spc), (unsigned)B);
     void* prof = profile_begin(MFAC_PROF_IMDCT, 4.0 * (double)B * ((double)L + (double)nf * N), stream);

@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/mfac.h"
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL) && !defined(__CUDA_ARCH_FEAT_SM101_ALL) && \
@@ -39,14 +41,31 @@
 namespace mfac {
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? MFAC_SUCCESS : -(1000 + (int)e); }
-inline int launch_status() { return cuda_status(cudaPeekAtLastError()); }
+// cudaGetLastError (not Peek): a failed launch is reported once and then cleared, so it cannot poison later calls of this
+// library or of the caller's own runtime (torch checks the same per-thread error slot).
+inline int launch_status() { return cuda_status(cudaGetLastError()); }
+
+// "Done once per device" flag for per-kernel function attributes (cudaFuncSetAttribute is per device, and entry points may
+// be called from several threads): bit d of the mask = configured on device d.  Two racing threads may both set the
+// (idempotent) attribute; neither can skip it.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask[2] = {};   // devices 0..127
+  int dev = 0;
+  bool need() {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 127) { dev = -1; return true; }
+    return ((mask[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+  }
+  void done() {
+    if (dev >= 0) mask[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+};
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T>
 __host__ __device__ constexpr T round_up(T a, T b) { return ceil_div(a, b) * b; }
 
-int num_sms();  // cached per process (device of first call)
+int num_sms();  // of the current device (cached per device)
 
 // ---------------------------------------------------------------------------------------
 // math

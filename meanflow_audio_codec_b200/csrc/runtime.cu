@@ -15,7 +15,7 @@ std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_simt{0};
 std::atomic<int> g_pair{getenv("MFAC_NO_PAIR_GEMM") ? 0 : 1};
 std::atomic<int> g_streamk{getenv("MFAC_NO_STREAM_K") ? 0 : 1};
-std::atomic<int> g_num_sms{0};
+std::atomic<int> g_num_sms[128] = {};   // per device
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -69,13 +69,13 @@ bool pair_gemm_enabled() { return g_pair.load(std::memory_order_relaxed) != 0; }
 bool stream_k_enabled() { return g_streamk.load(std::memory_order_relaxed) != 0; }
 
 int num_sms() {
-  int n = g_num_sms.load(std::memory_order_relaxed);
-  if (n > 0) return n;
   int dev = 0;
-  cudaGetDevice(&dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 127) dev = 0;
+  int n = g_num_sms[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   if (n <= 0) n = 148;
-  g_num_sms.store(n, std::memory_order_relaxed);
+  g_num_sms[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

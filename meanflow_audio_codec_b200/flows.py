@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import torch
 
@@ -40,19 +41,29 @@ def _to_device(tree, device):
 
 
 class _WeightCache:
-    """bf16 copies of the Dense kernels (what the tensor-core GEMMs read), refreshed when a leaf changes."""
+    """bf16 copies of the Dense kernels (what the tensor-core GEMMs read), refreshed when a leaf changes.
+
+    Entries are keyed by the identity of the source tensor and hold a weak reference to it: a different tensor that
+    happens to land on a freed address with the same shape (out-of-place parameter updates, a second checkpoint load)
+    can never be mistaken for the cached one, and entries whose source died are dropped.  ``keep`` only pins the
+    temporaries of ONE launch (``begin()`` clears it)."""
 
     def __init__(self):
         self._c = {}
         self.keep = []
 
+    def begin(self):
+        self.keep = []
+        if len(self._c) > 4096:
+            self._c = {k: v for k, v in self._c.items() if v[0]() is not None}
+
     def bf16(self, t: torch.Tensor) -> torch.Tensor:
-        key = (t.data_ptr(), tuple(t.shape))
-        hit = self._c.get(key)
-        if hit is None or hit[0] != t._version:
-            hit = (t._version, _lib.require_cuda(t, "kernel").to(torch.bfloat16).contiguous())
-            self._c[key] = hit
-        return hit[1]
+        hit = self._c.get(id(t))
+        if hit is None or hit[0]() is not t or hit[1] != t._version:
+            copy = _lib.require_cuda(t, "kernel").to(torch.bfloat16).contiguous()
+            hit = (weakref.ref(t), t._version, copy)
+            self._c[id(t)] = hit
+        return hit[2]
 
     def f32(self, t: torch.Tensor) -> torch.Tensor:
         t = _lib.require_cuda(t, "param")
@@ -126,7 +137,7 @@ class ConditionalMLPMixerFlow(_FlowBase):
         x, time, latents, B = self._check(x, time, latents)
         p = variables["params"]
         c = self._cache
-        c.keep = []
+        c.begin()
         blocks = (_lib.MixerBlockW * self.num_blocks)()
         for k in range(self.num_blocks):
             b, mb = p[f"blocks_{k}"], p[f"blocks_{k}"]["mixer_block"]
@@ -193,7 +204,7 @@ class ConditionalConvFlow(_FlowBase):
         x, time, latents, B = self._check(x, time, latents)
         p = variables["params"]
         c = self._cache
-        c.keep = []
+        c.begin()
         blocks = (_lib.ConvBlockW * self.num_blocks)()
         for k in range(self.num_blocks):
             b = p[f"blocks_{k}"]

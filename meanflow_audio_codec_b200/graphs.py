@@ -40,9 +40,17 @@ class GraphedTrainStep:
             self.state.model.flat_params(self.state.params).shadow()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # The captured launches hold RAW pointers into the model's loss/grad workspace.  ConditionalFlow.workspace keeps one
+        # buffer per kind and drops it when another batch size asks (validation, a last partial batch): pin the one the
+        # graph uses so that eviction there can never free memory the replays still write to.
+        from . import _lib
+        rows = self.x.shape[0]
+        self._ws_ref = state.model.workspace(_lib.WS_LOSS_GRAD, rows, dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
+        if state.model.workspace(_lib.WS_LOSS_GRAD, rows, dev).data_ptr() != self._ws_ref.data_ptr():
+            raise RuntimeError("loss/grad workspace changed during capture")
 
     def _flat(self):
         return self.state.model.flat_params(self.state.params).flat

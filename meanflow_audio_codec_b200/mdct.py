@@ -7,13 +7,15 @@ Same names, argument meaning and error behaviour as the reference:
   MDCTLayer / IMDCTLayer stereo handling                      (:547-693)
 Arrays are torch CUDA tensors where the reference takes ``jnp.ndarray``.
 
-``use_fft_threshold`` is kept for signature compatibility and ignored: the reference's
-FFT branch (taken for window_size >= 512 on non-Metal backends) is a different,
-non-invertible transform; this implementation always computes the
-direct-cosine definition, which is what the reference's test pins.
+``use_fft_threshold`` is kept for signature compatibility and never selects a different transform:
+the reference's FFT branch (taken for window_size >= threshold on non-Metal backends) is a
+different, non-invertible transform; this implementation always computes the
+direct-cosine definition, which is what the reference's test pins.  When a call WOULD have taken
+the reference's FFT branch a RuntimeWarning says so once per process ("MDCT branch").
 """
 from __future__ import annotations
 
+import warnings
 from dataclasses import dataclass
 
 import torch
@@ -41,8 +43,28 @@ class MDCTConfig:
             self.hop_size = self.window_size // 2
 
 
+_warned_fft_branch = False
+
+
+def _note_fft_branch(window_size, use_fft_threshold):
+    """The reference sends ``window_size >= use_fft_threshold`` (every shipped config: N = 512, default threshold 512) to an
+    FFT branch on CPU / CUDA backends (preprocessing/mdct.py:196-198,254-256) that is a DIFFERENT, non-invertible transform
+    (SURVEY.md R1); only Metal runs the direct cosine branch there.  This build always computes the direct cosine MDCT --
+    what the reference's own test pins and what its author ran.  Say so once instead of diverging silently: tokens of
+    such a config do not equal what the reference's CPU/CUDA FFT branch would have produced."""
+    global _warned_fft_branch
+    if window_size >= use_fft_threshold and not _warned_fft_branch:
+        _warned_fft_branch = True
+        warnings.warn(
+            f"mdct/imdct: window_size={window_size} >= use_fft_threshold={use_fft_threshold}: the reference would take its "
+            "FFT branch on CPU/CUDA (a different, non-invertible transform); libmfac always uses the direct cosine MDCT "
+            "(the reference's Metal / tested branch). Pass use_fft_threshold > window_size to state that intent explicitly.",
+            RuntimeWarning, stacklevel=3)
+
+
 def _resolve_config(config, window_size, hop_size, use_fft_threshold):
     if config is not None:
+        _note_fft_branch(config.window_size, config.use_fft_threshold)
         return config.window_size, config.hop_size, config.use_fft_threshold
     if window_size <= 0:
         raise ValueError(f"window_size must be positive, got {window_size}")
@@ -52,6 +74,7 @@ def _resolve_config(config, window_size, hop_size, use_fft_threshold):
         raise ValueError(f"use_fft_threshold must be positive, got {use_fft_threshold}")
     if hop_size is None:
         hop_size = window_size // 2
+    _note_fft_branch(window_size, use_fft_threshold)
     return window_size, hop_size, use_fft_threshold
 
 
