@@ -118,9 +118,20 @@ class ConditionalFlow:
         return self._slices
 
     # ---------------------------------------------------------------- params
-    def init(self, key=0, *args, device="cuda", **kwargs) -> dict:
+    def init(self, key=0, *args, device="cuda", on_device: bool = False, **kwargs) -> dict:
         """Flax-style init: lecun_normal kernels (truncated normal, var 1/fan_in), zero biases.
-        ``key`` is an int seed or a torch.Generator (the reference passes a jax PRNGKey)."""
+        ``key`` is an int seed or a torch.Generator (the reference passes a jax PRNGKey).
+        ``on_device=True`` draws the kernels with the device's generator instead of the host's (same distribution, another
+        stream): a 1 G-parameter geometry initialises in milliseconds instead of a minute of host RNG + upload."""
+        if on_device:
+            gen = torch.Generator(device=device).manual_seed(int(key) if not isinstance(key, torch.Generator) else key.initial_seed())
+            flat = torch.zeros(self.param_count(), dtype=torch.float32, device=device)
+            for path, (off, shp) in self.leaf_slices().items():
+                if path[-1] == "kernel":
+                    w = flat[off:off + math.prod(shp)]
+                    torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
+                    w.mul_(math.sqrt(1.0 / shp[0]) / 0.87962566103423978)
+            return {"params": FlatParams(self, flat).tree()}
         gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(int(key))
         flat = torch.zeros(self.param_count(), dtype=torch.float32)
         for path, (off, shp) in self.leaf_slices().items():
