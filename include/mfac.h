@@ -260,6 +260,14 @@ MFAC_API int mfac_comm_init(const void* id_bytes, int32_t rank, int32_t world);
 MFAC_API int mfac_comm_allreduce_sum_f32(float* buf, int64_t count, void* stream);
 MFAC_API int mfac_comm_destroy(void);
 
+/* ------------------------------------------------------------------ scheduling knob
+ * Batches of up to `rows` rows run the concurrent schedules of mfac_imf_loss_grad: the three forward evaluations of the iMF
+ * loss (trainers/loss_strategies.py:250-267) as independent kernel chains on the library's own side streams, and the
+ * weight-gradient GEMMs of the backward beside the critical dX chain; everything is joined back into the caller's stream
+ * before the call returns.  Default 4096 (env MFAC_CONC_MAX_ROWS); 0 = always the single-stream schedule.  The value also
+ * decides the layout mfac_workspace_bytes(MFAC_WS_LOSS_GRAD) sizes: change it before sizing the workspace, not between. */
+MFAC_API int mfac_set_concurrency_max_rows(int32_t rows);
+
 /* ------------------------------------------------------------------ test hooks
  * C[M,N] fp32 = A * B with bf16 operands through the production tcgen05 GEMM.
  * a_mn_major = 0: A stored [M,K] (K contiguous); 1: stored [K,M].

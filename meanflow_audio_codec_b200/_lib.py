@@ -107,6 +107,7 @@ PROTOTYPES = {
     "mfac_comm_init": (C.c_int, [_P, _I32, _I32]),
     "mfac_comm_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),
     "mfac_comm_destroy": (C.c_int, []),
+    "mfac_set_concurrency_max_rows": (C.c_int, [_I32]),
     "mfac_debug_gemm_bf16": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
     "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
     "mfac_debug_set_pair_gemm": (C.c_int, [_I32]),
@@ -144,6 +145,16 @@ def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = lib().mfac_status_string(int(status)).decode()
         raise MfacError(f"libmfac {what} failed: {msg} (status {status})")
+
+
+layout_epoch = 0   # bumped whenever a knob that changes workspace layouts is turned (cached workspaces are keyed on it)
+
+
+def set_concurrency_max_rows(rows: int) -> None:
+    """Batches of up to ``rows`` rows run ``mfac_imf_loss_grad``'s concurrent schedule (include/mfac.h); 0 switches it off."""
+    global layout_epoch
+    check(lib().mfac_set_concurrency_max_rows(int(rows)), "set_concurrency_max_rows")
+    layout_epoch += 1
 
 
 def launches() -> int:

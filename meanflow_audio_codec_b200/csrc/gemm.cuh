@@ -802,6 +802,29 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
   return launch_status();
 }
 
+// ---- intra-call concurrency (runtime.cu) ------------------------------------------------------------------------------
+// Small batches leave most of the machine idle: a 128-row GEMM occupies 10 of 148 SMs.  Entry points may therefore fork
+// independent kernel chains onto the library's own side streams and join them back before they return, so the caller
+// still sees ONE stream-ordered operation.  Streams and events are created once per (thread, device); forks are plain
+// event record / wait pairs, which stream capture turns into graph edges (GraphedTrainStep replays them as a DAG).
+struct ForkCtx {
+  static constexpr int kStreams = 3;
+  static constexpr int kEvents = 1024;
+  cudaStream_t side[kStreams];
+  cudaEvent_t ev[kEvents];
+  int next = 0;
+  cudaEvent_t next_event() { next = (next + 1) % kEvents; return ev[next]; }
+};
+ForkCtx* fork_ctx();          // nullptr when the streams / events cannot be created
+int concurrency_max_rows();   // batches up to this many rows use the concurrent schedules (MFAC_CONC_MAX_ROWS, default 4096; 0 = off)
+// everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
+inline int stream_after(ForkCtx* fc, cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = fc->next_event();
+  MFAC_CUDA_OK(cudaEventRecord(e, from));
+  MFAC_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+  return MFAC_SUCCESS;
+}
+
 bool pair_gemm_enabled();   // runtime.cu: on unless MFAC_NO_PAIR_GEMM is set / mfac_debug_set_pair_gemm(0)
 bool stream_k_enabled();    // runtime.cu: on unless MFAC_NO_STREAM_K is set
 

@@ -115,6 +115,9 @@ int ln_bwd(const LnBwdArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
   return launch_status();
 }
 
+// Batches this small run the concurrent schedules (independent kernel chains on the library's side streams, gemm.cuh: ForkCtx)
+inline bool concurrent_rows(int64_t B) { return concurrency_max_rows() > 0 && B <= concurrency_max_rows(); }
+
 // Scratch of one (unsaved) forward evaluation.
 struct FwdScratch {
   __nv_bfloat16 *gc, *m, *hin, *g;
@@ -195,6 +198,7 @@ struct LossGradPlan {
   // loss / backward
   float *row_loss, *g_x, *g_lat;
   __nv_bfloat16 *g_o, *g_a, *g_m, *g_ac, *g_latb, *g_ae;
+  __nv_bfloat16 *g_o2, *g_a2, *g_m2;   // second set (concurrent schedule: block k's weight gradients read set k & 1 on a side stream)
 
   void plan(Arena& ar, const Dims& d, int64_t B) {
     e = ar.take<float>(B * d.Dp);
@@ -238,6 +242,12 @@ struct LossGradPlan {
     g_ac = ar.take<__nv_bfloat16>(B * d.Ca);
     g_latb = ar.take<__nv_bfloat16>(B * d.Lp);
     g_ae = ar.take<__nv_bfloat16>(B * d.Hep);
+    g_o2 = g_o; g_a2 = g_a; g_m2 = g_m;
+    if (concurrent_rows(B)) {
+      g_o2 = ar.take<__nv_bfloat16>(B * d.Dp);
+      g_a2 = ar.take<__nv_bfloat16>(B * d.Ip);
+      g_m2 = ar.take<__nv_bfloat16>(B * d.Mp);
+    }
   }
 };
 
@@ -377,9 +387,17 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   const bool share = need_v && h * 4 >= B;
   if (!share) h = 0;
   const int Mu = (int)(B - h);   // rows whose u pass differs from their v pass
+  // Concurrent schedule for small batches (a 128-row GEMM fills 10 of 148 SMs): the three forward evaluations are
+  // independent chains -- v on the rows with r != t (unsaved), the saved primal pass with the (t, 0) conditioning on the rows with
+  // r == t, the saved primal u pass on the rows with r != t -- and run side by side on the library's side streams; the tangent
+  // pass follows on its own (it needs v and the u pass's activations); in the backward the weight gradients, bias column sums
+  // and the modulation-MLP input gradient leave the critical chain for a side stream.  Same kernels, same results.
+  ForkCtx* fc = concurrent_rows(B) ? fork_ctx() : nullptr;
+  const bool conc = fc != nullptr;
+  const bool conc_fwd = conc && need_v;
   // z_t -> xs[0] (u pass) and, for improved mean flow without sharing, v (v pass, in place); mean flow seeds the tangent
   // with e - x
-  PrepArgs pa{x, e, t, r, p.e, need_v && !share ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
+  PrepArgs pa{x, e, t, r, p.e, need_v && (!share || conc_fwd) ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
               p.xb, p.t, p.r, need_v ? p.cond_v : nullptr, p.cond_u, p.dcond_u, *cfg, B};
   launch_pdl(imf_prep_kernel, dim3((unsigned)B), dim3(ROW_THREADS), 0, s, pa, d);
   count_launch();
@@ -387,36 +405,79 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
   // one block of the saved primal pass over rows [r0, r0 + rows): activations go to the per-block buffers the tangent
   // pass and the backward read
-  auto primal_mod = [&](int k, int64_t r0, int rows) -> int {
+  auto primal_mod = [&](int k, int64_t r0, int rows, cudaStream_t st) -> int {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
     SavedBlock& sb = p.blk[k];
-    return gemm_linear_bf16(sb.gc + r0 * d.Ca, d.Ca, w + d.s_c2w, rows, d.Mp, d.Cp, bias + d.b_c2, sb.m + r0 * d.Mp, d.Mp, s);
+    return gemm_linear_bf16(sb.gc + r0 * d.Ca, d.Ca, w + d.s_c2w, rows, d.Mp, d.Cp, bias + d.b_c2, sb.m + r0 * d.Mp, d.Mp, st);
   };
   // keep: rows (relative to r0) whose pre-activation a and block output o are stored for the tangent pass / backward
-  auto primal_mlp = [&](int k, int64_t r0, int rows, int keep) -> int {
+  auto primal_mlp = [&](int k, int64_t r0, int rows, int keep, cudaStream_t st) -> int {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
     SavedBlock& sb = p.blk[k];
     float* x_in = p.xs + (int64_t)k * B * d.Dp + r0 * d.Dp;
     float* x_out = p.xs + (int64_t)(k + 1) * B * d.Dp + r0 * d.Dp;
     MFAC_OK(gemm_fwd(sb.hin + r0 * d.Ip, d.Ip, w + d.s_m1w, rows, d.Ip, d.Ip,
-                     EpiBiasGelu{bias + d.b_m1, sb.g + r0 * d.Ip, sb.a + r0 * d.Ip, d.Ip, keep}, s));
+                     EpiBiasGelu{bias + d.b_m1, sb.g + r0 * d.Ip, sb.a + r0 * d.Ip, d.Ip, keep}, st));
     return gemm_fwd(sb.g + r0 * d.Ip, d.Ip, w + d.s_m2w, rows, d.Dp, d.Ip,
-                    EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb, keep}, s);
+                    EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb, keep}, st);
   };
+  // the saved primal pass (all blocks) over rows [r0, r0 + rows) with conditioning rows `cond`
+  auto saved_pass = [&](const __nv_bfloat16* cond, int64_t r0, int rows, int keep, cudaStream_t st) -> int {
+    MFAC_OK(gemm_bias_gelu(cond + r0 * d.Cp, d.Cp, sh.w + d.s_c1all, rows, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all + r0 * d.Ca,
+                           p.ac_all + r0 * d.Ca, d.Ca, st));
+    for (int k = 0; k < d.nb; ++k) {
+      SavedBlock& sb = p.blk[k];
+      MFAC_OK(primal_mod(k, r0, rows, st));
+      LnModArgs la{p.lat + r0 * d.Lp, p.xs + (int64_t)k * B * d.Dp + r0 * d.Dp, sb.m + r0 * d.Mp, sb.hin + r0 * d.Ip, nullptr, nullptr,
+                   nullptr, sb.mu + r0, sb.rstd + r0, d.Mp};
+      MFAC_OK(lnmod(false, la, d, rows, st));
+      MFAC_OK(primal_mlp(k, r0, rows, keep, st));
+    }
+    return MFAC_SUCCESS;
+  };
+  // one block of the tangent pass over rows [h, B); with_primal: the fused AdaLN kernel also produces the primal's hin / statistics
+  auto tangent_block = [&](int k, bool with_primal, cudaStream_t st) -> int {
+    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
+    SavedBlock& sb = p.blk[k];
+    float* x_in = p.xs + (int64_t)k * B * d.Dp + h * d.Dp;
+    const float* xd_in = (k == 0 ? p.v : p.xd) + h * d.Dp;
+    MFAC_OK(gemm_linear_bf16(p.gcd + h * d.Ca + k * d.Cp, d.Ca, w + d.s_c2w, Mu, d.Mp, d.Cp, nullptr, p.md + h * d.Mp, d.Mp, st));
+    LnModArgs la{p.lat + h * d.Lp, x_in, sb.m + h * d.Mp, with_primal ? sb.hin + h * d.Ip : nullptr, xd_in, p.md + h * d.Mp,
+                 p.hind + h * d.Ip, with_primal ? sb.mu + h : nullptr, with_primal ? sb.rstd + h : nullptr, d.Mp};
+    MFAC_OK(lnmod(true, la, d, Mu, st));
+    // the tangent GEMMs read the primal pre-activation a and block output o: primal first
+    if (with_primal) MFAC_OK(primal_mlp(k, h, Mu, Mu, st));
+    MFAC_OK(gemm_fwd(p.hind + h * d.Ip, d.Ip, w + d.s_m1w, Mu, d.Ip, d.Ip, EpiMulDgelu{sb.a + h * d.Ip, p.gd + h * d.Ip, d.Ip}, st));
+    return gemm_fwd(p.gd + h * d.Ip, d.Ip, w + d.s_m2w, Mu, d.Dp, d.Ip,
+                    EpiBlockOutTangent{sb.m + h * d.Mp, p.md + h * d.Mp, sb.o + h * d.Dp, xd_in, p.xd + h * d.Dp, d.Mp, d.Dp,
+                                       2 * d.Ip, inv_nb}, st);
+  };
+  if (conc_fwd) {
+    // ---- three independent forward chains side by side, then the tangent chain
+    cudaStream_t sV = fc->side[0], sS = fc->side[1];
+    MFAC_OK(stream_after(fc, s, sV));
+    MFAC_OK(stream_after(fc, s, sS));
+    if (Mu > 0) {   // v = f(z, [t, 0], lat) on the rows with r != t (in place on p.v, nothing kept)
+      MFAC_OK(forward_pass(d, sh, p.cond_v + h * d.Cp, p.lat + h * d.Lp, p.v + h * d.Dp, Mu, p.fs, sV));
+      MFAC_OK(saved_pass(p.cond_u, h, Mu, Mu, s));
+      if (tangent)
+        MFAC_OK(gemm_fwd(p.dcond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp,
+                         EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, s));
+    }
+    if (h > 0) MFAC_OK(saved_pass(p.cond_v, 0, (int)h, (int)h, sS));   // rows with r == t: u IS v
+    MFAC_OK(stream_after(fc, sV, s));
+    MFAC_OK(stream_after(fc, sS, s));
+    if (h > 0 && aux && aux->v)
+      MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.xs + (int64_t)d.nb * B * d.Dp, (size_t)h * d.Dp * 4, cudaMemcpyDeviceToDevice, s));
+    for (int k = 0; k < d.nb && Mu > 0 && tangent; ++k) MFAC_OK(tangent_block(k, false, s));
+  } else {
   // ---- v = f(z, [t, 0], lat)
   if (share) {
     // saved primal pass over ALL rows with the (t, 0) conditioning: v for every row, and already u (with every
     // activation the tangent pass and the backward need) for rows [0, h)
-    MFAC_OK(gemm_bias_gelu(p.cond_v, d.Cp, sh.w + d.s_c1all, M, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all, p.ac_all, d.Ca, s));
-    for (int k = 0; k < d.nb; ++k) {
-      SavedBlock& sb = p.blk[k];
-      MFAC_OK(primal_mod(k, 0, M));
-      LnModArgs la{p.lat, p.xs + (int64_t)k * B * d.Dp, sb.m, sb.hin, nullptr, nullptr, nullptr, sb.mu, sb.rstd, d.Mp};
-      MFAC_OK(lnmod(false, la, d, B, s));
-      MFAC_OK(primal_mlp(k, 0, M, (int)h));   // rows [h, B) get their a / o from the u pass below
-    }
+    MFAC_OK(saved_pass(p.cond_v, 0, M, (int)h, s));   // rows [h, B) get their a / o from the u pass below
     // v is the tangent seed of the rows that still get a u pass (and an optional test output for all rows)
     const int64_t v0 = (aux && aux->v) ? 0 : h;
     if (v0 < B)
@@ -438,25 +499,18 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
                        EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, s));
   }
   for (int k = 0; k < d.nb && Mu > 0; ++k) {
-    const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
-    SavedBlock& sb = p.blk[k];
-    float* x_in = p.xs + (int64_t)k * B * d.Dp + h * d.Dp;
-    const float* xd_in = (k == 0 ? p.v : p.xd) + h * d.Dp;
-    // modulation, primal and tangent
-    MFAC_OK(primal_mod(k, h, Mu));
-    if (tangent)
-      MFAC_OK(gemm_linear_bf16(p.gcd + h * d.Ca + k * d.Cp, d.Ca, w + d.s_c2w, Mu, d.Mp, d.Cp, nullptr, p.md + h * d.Mp, d.Mp, s));
-    LnModArgs la{p.lat + h * d.Lp, x_in, sb.m + h * d.Mp, sb.hin + h * d.Ip, xd_in, p.md + h * d.Mp, p.hind + h * d.Ip,
-                 sb.mu + h, sb.rstd + h, d.Mp};
-    MFAC_OK(lnmod(tangent, la, d, Mu, s));
-    // the tangent GEMMs read the primal pre-activation a and block output o: primal first
-    MFAC_OK(primal_mlp(k, h, Mu, Mu));
     if (tangent) {
-      MFAC_OK(gemm_fwd(p.hind + h * d.Ip, d.Ip, w + d.s_m1w, Mu, d.Ip, d.Ip, EpiMulDgelu{sb.a + h * d.Ip, p.gd + h * d.Ip, d.Ip}, s));
-      MFAC_OK(gemm_fwd(p.gd + h * d.Ip, d.Ip, w + d.s_m2w, Mu, d.Dp, d.Ip,
-                       EpiBlockOutTangent{sb.m + h * d.Mp, p.md + h * d.Mp, sb.o + h * d.Dp, xd_in, p.xd + h * d.Dp, d.Mp, d.Dp,
-                                          2 * d.Ip, inv_nb}, s));
+      MFAC_OK(primal_mod(k, h, Mu, s));
+      MFAC_OK(tangent_block(k, true, s));
+    } else {
+      SavedBlock& sb = p.blk[k];
+      MFAC_OK(primal_mod(k, h, Mu, s));
+      LnModArgs la{p.lat + h * d.Lp, p.xs + (int64_t)k * B * d.Dp + h * d.Dp, sb.m + h * d.Mp, sb.hin + h * d.Ip, nullptr, nullptr,
+                   nullptr, sb.mu + h, sb.rstd + h, d.Mp};
+      MFAC_OK(lnmod(false, la, d, Mu, s));
+      MFAC_OK(primal_mlp(k, h, Mu, Mu, s));
     }
+  }
   }
   if (h > 0 && tangent && aux && aux->dudt) MFAC_CUDA_OK(cudaMemsetAsync(p.xd, 0, (size_t)h * d.Dp * 4, s));  // reported as 0
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
@@ -469,45 +523,63 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   // ---- backward through the primal u rows (weight gradients accumulate split-K partials atomically)
   MFAC_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)d.total * 4, s));
   MFAC_CUDA_OK(cudaMemsetAsync(p.g_lat, 0, (size_t)B * d.Lp * 4, s));
+  // Concurrent schedule: the critical chain (block-output backward -> two dX GEMMs -> LayerNorm backward) stays on `s`; the
+  // weight gradients, the remaining bias column sums and the modulation-MLP input gradient of block k run on a side stream from
+  // transient set k & 1, which the critical chain only overwrites again two blocks later (after that block's side work).
+  cudaStream_t sW = conc ? fc->side[2] : s;
+  cudaEvent_t side_done[2] = {nullptr, nullptr};
   for (int k = d.nb - 1; k >= 0; --k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     SavedBlock& sb = p.blk[k];
     float* gk = grads + (int64_t)k * d.blk_stride;
     const float* x_in = p.xs + (int64_t)k * B * d.Dp;
+    const int par = conc ? (k & 1) : 0;
+    __nv_bfloat16* g_o = par ? p.g_o2 : p.g_o;
+    __nv_bfloat16* g_a = par ? p.g_a2 : p.g_a;
+    __nv_bfloat16* g_m = par ? p.g_m2 : p.g_m;
+    if (conc && side_done[par]) MFAC_CUDA_OK(cudaStreamWaitEvent(s, side_done[par], 0));   // set `par` is free again
     // g_o, g_s2 and both of their bias-gradient column sums (db2, the s2 third of dbc2) in one pass
     launch_pdl(bwd_block_out_vec_kernel, dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), dim3(256), 0, s,
-               (const float*)p.g_x, (const __nv_bfloat16*)sb.m, (const __nv_bfloat16*)sb.o, p.g_o, p.g_m, gk + d.o_m2b, gk + d.o_c2b, d, B,
+               (const float*)p.g_x, (const __nv_bfloat16*)sb.m, (const __nv_bfloat16*)sb.o, g_o, g_m, gk + d.o_m2b, gk + d.o_c2b, d, B,
                sweep_next());
     count_launch();
-    MFAC_OK(gemm_dw(sb.g, d.Ip, p.g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, s));
+    if (conc) MFAC_OK(stream_after(fc, s, sW));
+    MFAC_OK(gemm_dw(sb.g, d.Ip, g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, sW));
     // Unpadded geometries: the dX epilogues that write g_a and g_shift also accumulate their column sums (db1 and the shift
     // third of dbc2) -- no separate pass over those tensors.
     const bool fused_colsum = d.I == d.Ip;
     if (fused_colsum) {
       EpiMulDgeluColsum ep;
-      ep.a = sb.a; ep.out = p.g_a; ep.ld = d.Ip; ep.colsum = gk + d.o_m1b;
-      MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, ep, s));
+      ep.a = sb.a; ep.out = g_a; ep.ld = d.Ip; ep.colsum = gk + d.o_m1b;
+      MFAC_OK(gemm_dx(g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, ep, s));
     } else {
-      MFAC_OK(gemm_dx(p.g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, p.g_a, d.Ip}, s));
+      MFAC_OK(gemm_dx(g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, g_a, d.Ip}, s));
     }
-    MFAC_OK(gemm_dw(sb.hin, d.Ip, p.g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, s));
-    if (!fused_colsum) MFAC_OK(colsum(p.g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, s));
+    if (conc) MFAC_OK(stream_after(fc, s, sW));
+    MFAC_OK(gemm_dw(sb.hin, d.Ip, g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, sW));
+    if (!fused_colsum) MFAC_OK(colsum(g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, sW));
     // g_hin = g_a W1^T goes out in bf16 straight into g_m[:, Ip:2Ip]: it IS the shift gradient (hin = (1+s1) n + shift)
     if (fused_colsum) {
       EpiLinearBf16Colsum ep;
-      ep.bias = nullptr; ep.out = p.g_m + d.Ip; ep.ld = d.Mp; ep.colsum = gk + d.o_c2b + d.I;
-      MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, ep, s));
+      ep.bias = nullptr; ep.out = g_m + d.Ip; ep.ld = d.Mp; ep.colsum = gk + d.o_c2b + d.I;
+      MFAC_OK(gemm_dx(g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, ep, s));
     } else {
-      MFAC_OK(gemm_dx(p.g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, p.g_m + d.Ip, d.Mp}, s));
+      MFAC_OK(gemm_dx(g_a, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, EpiLinearBf16{nullptr, g_m + d.Ip, d.Mp}, s));
     }
-    LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, p.g_m, p.g_lat, p.g_x};
+    LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
-    MFAC_OK(gemm_dw(sb.gc, d.Ca, p.g_m, d.Mp, d.Cp, d.Mp, M,
-                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, s));
+    if (conc) MFAC_OK(stream_after(fc, s, sW));
+    MFAC_OK(gemm_dw(sb.gc, d.Ca, g_m, d.Mp, d.Cp, d.Mp, M,
+                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, sW));
     // s1 third (and the shift third where it was not fused above)
-    MFAC_OK(colsum(p.g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, s, fused_colsum ? d.Ip : 2 * d.Ip));
-    MFAC_OK(gemm_dx(p.g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac + k * d.Cp, d.Ca}, s));
+    MFAC_OK(colsum(g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, sW, fused_colsum ? d.Ip : 2 * d.Ip));
+    MFAC_OK(gemm_dx(g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac + k * d.Cp, d.Ca}, sW));
+    if (conc) {
+      side_done[par] = fc->next_event();
+      MFAC_CUDA_OK(cudaEventRecord(side_done[par], sW));
+    }
     if (k == 0) {
+      if (conc) MFAC_OK(stream_after(fc, sW, s));   // every block's side work (in order on sW) is done
       // first modulation layer, all blocks at once: dW = cond^T @ g_ac_all, db = column sums
       MFAC_OK(gemm_dw(p.cond_u, d.Cp, p.g_ac, d.Ca, d.Cp, d.Ca, M, EpiGradStoreC1{grads, d}, s));
       MFAC_OK(colsum(p.g_ac, d.Ca, B, grads, MAP_C1ALL, 0, d, s));

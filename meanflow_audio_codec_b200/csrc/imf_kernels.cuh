@@ -208,7 +208,7 @@ struct LnModArgs {
   const float* lat;          // [B, Lp] or null (zeros)
   const float* x;            // [B, Dp]
   const __nv_bfloat16* m;    // [B, Mp]
-  __nv_bfloat16* hin;        // [B, Ip]
+  __nv_bfloat16* hin;        // [B, Ip]; may be null for TANGENT (tangent-only pass: hin / mu / rstd come from the primal pass)
   const float* xd;           // tangent
   const __nv_bfloat16* md;   // tangent
   __nv_bfloat16* hind;       // tangent
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(ROW_THREADS) lnmod_kernel(LnModArgs a, Dims d)
         hd = __bfloat162float(mdrow[p]) * n + (1.0f + s1) * nd + __bfloat162float(mdrow[d.Ip + p]);
       }
     }
-    a.hin[b * d.Ip + p] = __float2bfloat16(h);
+    if (a.hin) a.hin[b * d.Ip + p] = __float2bfloat16(h);   // null: tangent-only pass (the primal pass stored hin already)
     if (TANGENT) a.hind[b * d.Ip + p] = __float2bfloat16(hd);
   }
 }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(TANGENT ? 128 : 256, TANGENT ? 3 : 1) lnmod_ve
       n[q] = (c[i][q] - mu) * rstd;
       h[q] = (1.0f + s1[q]) * n[q] + sh[q];
     }
-    st8_bf16(a.hin + b * d.Ip + col, h);
+    if (!TANGENT || a.hin) st8_bf16(a.hin + b * d.Ip + col, h);   // hin == null: tangent-only pass
     if (TANGENT) {
       float s1d[8], shd[8];
       cvt8_bf16(r_s1d[i], s1d);

@@ -79,6 +79,37 @@ int num_sms() {
   return n;
 }
 
+namespace {
+struct ForkSlot {
+  int dev = -1;
+  bool ok = false;
+  ForkCtx ctx;
+};
+}  // namespace
+
+ForkCtx* fork_ctx() {
+  static thread_local std::vector<ForkSlot*> slots;   // one per device this thread has used (never freed: process lifetime)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (ForkSlot* sl : slots)
+    if (sl->dev == dev) return sl->ok ? &sl->ctx : nullptr;
+  ForkSlot* sl = new ForkSlot();
+  sl->dev = dev;
+  sl->ok = true;
+  for (int i = 0; i < ForkCtx::kStreams && sl->ok; ++i)
+    sl->ok = cudaStreamCreateWithFlags(&sl->ctx.side[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < ForkCtx::kEvents && sl->ok; ++i)
+    sl->ok = cudaEventCreateWithFlags(&sl->ctx.ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!sl->ok) cudaGetLastError();
+  slots.push_back(sl);
+  return sl->ok ? &sl->ctx : nullptr;
+}
+
+namespace {
+std::atomic<int> g_conc_rows{getenv("MFAC_CONC_MAX_ROWS") ? atoi(getenv("MFAC_CONC_MAX_ROWS")) : 4096};
+}
+int concurrency_max_rows() { return g_conc_rows.load(std::memory_order_relaxed); }
+
 int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                       int box_outer, int swizzle_bytes) {
   std::call_once(g_encode_once, resolve_encode);
@@ -143,6 +174,11 @@ int mfac_debug_set_simt_gemm(int32_t on) {
 
 int mfac_debug_set_stream_k(int32_t on) {
   mfac::g_streamk.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+int mfac_set_concurrency_max_rows(int32_t rows) {
+  mfac::g_conc_rows.store(rows < 0 ? 0 : rows);
   return MFAC_SUCCESS;
 }
 

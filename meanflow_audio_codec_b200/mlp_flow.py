@@ -160,7 +160,7 @@ class ConditionalFlow:
         return FlatParams(self, torch.cat(parts))
 
     def workspace(self, kind: int, B: int, device) -> torch.Tensor:
-        key = (kind, int(B), str(device))
+        key = (kind, int(B), str(device), _lib.layout_epoch)
         ws = self._ws.get(key)
         if ws is None:
             n = _lib.lib().mfac_workspace_bytes(kind, C.byref(self.dims), int(B))

@@ -505,3 +505,34 @@ def test_reference_training_loop_drops_in(cuda, tmp_path):
     smp = m.sample(state.apply_fn, D, state.params, cfg.sample_seed, latents=lat, n_steps=2)    # train.py:371-380
     audio = tok.detokenize(smp.reshape(cfg.batch_size, -1, tok.config.window_size))             # train.py:387
     assert audio.shape == (cfg.batch_size, 1280) and torch.isfinite(audio).all()
+
+
+@pytest.mark.parametrize("method", ["improved_mean_flow", "mean_flow", "flow_matching"])
+@pytest.mark.parametrize("B", [8, 333])
+def test_concurrent_schedule_matches_single_stream(cuda, method, B):
+    """Small batches fork the three forward evaluations and the backward's weight gradients onto the library's side streams
+    (include/mfac.h: mfac_set_concurrency_max_rows).  Same kernels on the same rows: loss, u, v, du/dt are bit-identical to
+    the single-stream schedule, gradients agree to split-K summation-order noise -- with and without the r == t sharing."""
+    import meanflow_audio_codec_b200 as m
+    from meanflow_audio_codec_b200 import _lib
+    D, L, C, nb = 128, 64, 32, 3
+    p_np = oracle_params(D, L, C, nb, seed=5)
+    model = m.ConditionalFlow(noise_dimension=D, condition_dimension=C, num_blocks=nb, latent_dimension=L)
+    state = m.TrainState.create(apply_fn=model.apply, params=to_device_tree(p_np), tx=m.adamw(1e-4, 1e-4))
+    strat = {"improved_mean_flow": m.ImprovedMeanFlowLoss, "mean_flow": m.MeanFlowLoss, "flow_matching": m.FlowMatchingLoss}[method]()
+    x = torch.randn(B, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    res = {}
+    try:
+        for rows in (0, 4096):
+            _lib.set_concurrency_max_rows(rows)
+            for share in (0, -1):
+                res[(rows, share)] = strat.compute_loss(state, 3, x, return_aux=True, rows_r_equals_t=share)
+                torch.cuda.synchronize()
+    finally:
+        _lib.set_concurrency_max_rows(4096)
+    for share in (0, -1):
+        (l0, g0, a0), (l1, g1, a1) = res[(0, share)], res[(4096, share)]
+        assert float(l0) == float(l1)
+        for k in ("e", "t", "r", "u", "v", "dudt", "per_example"):
+            assert torch.equal(a0[k], a1[k]), (k, share)
+        assert rel_l2(g1.flat.cpu().numpy(), g0.flat.cpu().numpy()) < 1e-5
