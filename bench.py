@@ -303,6 +303,8 @@ def run_mfac(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(dp.local_rank)
     dev = torch.device("cuda", dp.local_rank)
+    if dp.enabled and os.environ.get("MFAC_DP_TORCH", "0") != "1":
+        dp.init_library_comm()    # the fused step then all-reduces through libmfac's own communicator (mfac_comm_*)
     T = args.noise_dimension
     nf, D = token_dim(T)
     pk = peaks()

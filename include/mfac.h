@@ -184,6 +184,23 @@ MFAC_API int mfac_adamw_step_dev(const MfacMlpDims* dims, float* params, const f
                         uint64_t* count_dev, float* scratch_dev, float lr, float b1, float b2, float eps, float weight_decay,
                         float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ fused training step
+ * ref: train_step (trainers/training_steps.py:15-61) = compute_loss + TrainState.apply_gradients with optax.adamw
+ * (trainers/train.py:236).  One call: mfac_imf_loss_grad's schedule, and the AdamW update (with the bf16 shadow refresh)
+ * applied slice by slice as the backward finalises each block's gradient -- for small batches on the library's side stream,
+ * under the rest of the backward -- instead of one pass over all parameters afterwards.  world > 1: every slice is first
+ * sum-all-reduced over the communicator of mfac_comm_init (NCCL on the stream the slice became final on, so the exchange
+ * overlaps the remaining backward) and scaled by 1 / world.  `count` = steps already taken; count_dev / scratch_dev select the
+ * graph-capturable form of mfac_adamw_step_dev (count is then ignored).  grads is caller-provided scratch of the parameter
+ * vector's size and holds the (summed) gradient afterwards. */
+typedef struct MfacAdamWConfig {
+  float lr, b1, b2, eps, weight_decay;   /* optax.adamw: 1e-4 (config base_lr), 0.9, 0.999, 1e-8, 1e-4 */
+} MfacAdamWConfig;
+MFAC_API int mfac_imf_train_step(const MfacMlpDims* dims, const MfacImfConfig* cfg, const MfacAdamWConfig* opt, float* params,
+                        void* shadow, float* mu, float* nu, int64_t count, uint64_t* count_dev, float* scratch_dev,
+                        const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
+                        const MfacImfAux* aux, int64_t B, int32_t world, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ samplers
  * MFAC_SAMPLE_HEUN  ref: evaluators/sampling.py:5-95 (h = 0, grid linspace(1,0,n), dt = 1/n).
  * MFAC_SAMPLE_MF    mean-flow few-step rule x_r = x_t - (t-r) u(x_t,[t,t-r]) on a uniform grid
@@ -281,6 +298,11 @@ MFAC_API int mfac_debug_set_stream_k(int32_t on);
 /* 0 = never use the CTA-pair (cta_group::2) GEMM kernel; 1 (default) = use it where it pays. */
 MFAC_API int mfac_debug_set_pair_gemm(int32_t on);
 MFAC_API int mfac_debug_counters(int64_t* kernel_launches);
+/* Phase timeline of the training step (debug): while on, mfac_imf_loss_grad / mfac_imf_train_step record an event at each
+ * phase boundary (1 prologue+encoder done, 2 forward chains joined, 3 tangent done, 4 loss done, 5..: after each backward
+ * block, 90 backward done, 99 end); collect returns ids and milliseconds since the first mark and clears the list. */
+MFAC_API int mfac_debug_phase_marks(int32_t on);
+MFAC_API int mfac_debug_phase_collect(int32_t* ids, float* ms_since_first, int32_t cap);
 
 /* ------------------------------------------------------------------ per-kernel timing (bench.py roofline)
  * While enabled, every launch of a profiled kernel family is bracketed by CUDA events on its own

@@ -33,6 +33,10 @@ class ImfConfig(C.Structure):
     ]
 
 
+class AdamWConfig(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("lr", "b1", "b2", "eps", "weight_decay")]
+
+
 GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
 
 
@@ -95,6 +99,8 @@ PROTOTYPES = {
     "mfac_mlp_forward": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _I64, _P, C.c_size_t, _P]),
     "mfac_imf_loss_grad": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), _P, _P, _P, _P, _P, _P, _P, _P,
                                      C.POINTER(ImfAux), _I64, _P, C.c_size_t, _P]),
+    "mfac_imf_train_step": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), C.POINTER(AdamWConfig), _P, _P, _P, _P, _I64, _P, _P,
+                                      _P, _P, _P, _P, _P, _P, C.POINTER(ImfAux), _I64, _I32, _P, C.c_size_t, _P]),
     "mfac_adamw_step": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_adamw_step_dev": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_sample": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I32, _I32, _F, C.c_uint64, _P, _I64, _P,
@@ -112,6 +118,8 @@ PROTOTYPES = {
     "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
     "mfac_debug_set_pair_gemm": (C.c_int, [_I32]),
     "mfac_debug_set_stream_k": (C.c_int, [_I32]),
+    "mfac_debug_phase_marks": (C.c_int, [_I32]),
+    "mfac_debug_phase_collect": (C.c_int, [C.POINTER(_I32), C.POINTER(C.c_float), _I32]),
     "mfac_debug_counters": (C.c_int, [C.POINTER(_I64)]),
     "mfac_profile_enable": (C.c_int, [_I32]),
     "mfac_profile_collect": (C.c_int, [C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -39,19 +39,28 @@ struct AdamArgs {
 };
 
 // t = *count + 1;  bc = {1 / (1 - b1^t), 1 / (1 - b2^t)};  ++*count
-__global__ void adamw_bias_correction_kernel(uint64_t* count, float* bc, float b1, float b2) {
+__global__ void adamw_bias_correction_kernel(uint64_t* count, float* bc, float b1, float b2, int advance) {
   const double t = (double)(*count) + 1.0;
   bc[0] = (float)(1.0 / (1.0 - pow((double)b1, t)));
   bc[1] = (float)(1.0 / (1.0 - pow((double)b2, t)));
-  *count += 1;
+  if (advance) *count += 1;
 }
+__global__ void advance_count_kernel(uint64_t* count) { *count += 1; }
 
-__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d) {
-  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i0 >= d.total) return;
+// Segment j (= blockIdx.y) covers the flat indices [seg_off + j * seg_stride, + seg_cnt): the whole vector is one segment;
+// a training step that applies the update slice by slice (mfac_imf_train_step) passes one block's slice, or the nb short
+// first-modulation-layer slices in one launch.  Thread 0 of a segment takes the unaligned head so that every other thread
+// works on a 16-byte aligned quad.
+__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d, int64_t seg_off, int64_t seg_cnt, int64_t seg_stride) {
+  const int64_t begin = seg_off + (int64_t)blockIdx.y * seg_stride, end = begin + seg_cnt;
+  const int64_t a4 = (begin + 3) & ~(int64_t)3;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i0 = tid == 0 ? begin : a4 + (tid - 1) * 4;
+  int64_t lim = tid == 0 ? (a4 < end ? a4 : end) : end;
+  if (i0 >= lim) return;
   float p[4], g[4], m[4], v[4];
   const float inv_bc1 = a.bc_dev ? a.bc_dev[0] : a.inv_bc1, inv_bc2 = a.bc_dev ? a.bc_dev[1] : a.inv_bc2;
-  const bool full = i0 + 4 <= d.total;
+  const bool full = tid != 0 && i0 + 4 <= lim;
   if (full) {
     const float4 p4 = *reinterpret_cast<const float4*>(a.p + i0), g4 = *reinterpret_cast<const float4*>(a.g + i0);
     const float4 m4 = *reinterpret_cast<const float4*>(a.mu + i0), v4 = *reinterpret_cast<const float4*>(a.nu + i0);
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d) {
     v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
   } else {
     for (int q = 0; q < 4; ++q) {
-      const bool ok = i0 + q < d.total;
+      const bool ok = i0 + q < lim;
       p[q] = ok ? a.p[i0 + q] : 0.f; g[q] = ok ? a.g[i0 + q] : 0.f;
       m[q] = ok ? a.mu[i0 + q] : 0.f; v[q] = ok ? a.nu[i0 + q] : 0.f;
     }
@@ -79,12 +88,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, Dims d) {
     *reinterpret_cast<float4*>(a.mu + i0) = make_float4(m[0], m[1], m[2], m[3]);
     *reinterpret_cast<float4*>(a.nu + i0) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    for (int q = 0; q < 4 && i0 + q < d.total; ++q) { a.p[i0 + q] = p[q]; a.mu[i0 + q] = m[q]; a.nu[i0 + q] = v[q]; }
+    for (int q = 0; q < 4 && i0 + q < lim; ++q) { a.p[i0 + q] = p[q]; a.mu[i0 + q] = m[q]; a.nu[i0 + q] = v[q]; }
   }
   if (a.sw) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (i0 + q >= d.total) break;
+      if (i0 + q >= lim) break;
       const ShadowSlot s = shadow_slot_of(d, i0 + q);
       if (s.is_bias) a.sb[s.idx] = p[q];
       else a.sw[s.idx] = __float2bfloat16(p[q]);
@@ -143,6 +152,49 @@ int mfac_mlp_cast_params(const MfacMlpDims* dims, const float* params, void* sha
   return mfac::launch_status();
 }
 
+}  // extern "C"
+
+namespace mfac {
+// One launch over nseg segments [seg_off + j * seg_stride, + seg_cnt) of the flat parameter vector (imf.cu: train step).
+int adamw_segments(const Dims& d, const AdamWLaunch& h, int64_t seg_off, int64_t seg_cnt, int64_t seg_stride, int nseg,
+                   cudaStream_t s) {
+  if (seg_cnt <= 0 || nseg <= 0) return MFAC_SUCCESS;
+  AdamArgs a;
+  a.p = h.params; a.g = h.grads; a.mu = h.mu; a.nu = h.nu;
+  a.sw = reinterpret_cast<__nv_bfloat16*>(h.shadow);
+  a.sb = h.shadow ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h.shadow) + d.bias_section_bytes_offset) : nullptr;
+  a.lr = h.lr; a.b1 = h.b1; a.b2 = h.b2; a.eps = h.eps; a.wd = h.weight_decay; a.gscale = h.grad_scale;
+  a.inv_bc1 = h.inv_bc1; a.inv_bc2 = h.inv_bc2; a.bc_dev = h.bc_dev;
+  const int64_t threads = ceil_div<int64_t>(seg_cnt, 4) + 2;
+  void* prof = profile_begin(MFAC_PROF_ADAMW, (h.shadow ? 30.0 : 28.0) * (double)seg_cnt * nseg, s);
+  adamw_kernel<<<dim3((unsigned)ceil_div<int64_t>(threads, 256), (unsigned)nseg), 256, 0, s>>>(a, d, seg_off, seg_cnt, seg_stride);
+  profile_end(prof, s);
+  count_launch();
+  return launch_status();
+}
+// host-side bias correction for step count `count` (steps already taken), or the device-side form for graph replay
+int adamw_prepare(AdamWLaunch& h, int64_t count, uint64_t* count_dev, float* scratch_dev, cudaStream_t s, bool advance) {
+  const double c = (double)count + 1.0;
+  h.inv_bc1 = (float)(1.0 / (1.0 - std::pow((double)h.b1, c)));
+  h.inv_bc2 = (float)(1.0 / (1.0 - std::pow((double)h.b2, c)));
+  h.bc_dev = nullptr;
+  if (count_dev) {
+    if (!scratch_dev) return MFAC_ERR_NULL;
+    adamw_bias_correction_kernel<<<1, 1, 0, s>>>(count_dev, scratch_dev, h.b1, h.b2, advance ? 1 : 0);
+    count_launch();
+    h.bc_dev = scratch_dev;
+  }
+  return launch_status();
+}
+int adamw_advance(uint64_t* count_dev, cudaStream_t s) {
+  advance_count_kernel<<<1, 1, 0, s>>>(count_dev);
+  count_launch();
+  return launch_status();
+}
+}  // namespace mfac
+
+extern "C" {
+
 namespace {
 int adamw_launch(const MfacMlpDims* dims, float* params, const float* grads, float* mu, float* nu, void* shadow, int64_t count,
                  uint64_t* count_dev, float* scratch_dev, float lr, float b1, float b2, float eps, float weight_decay,
@@ -152,27 +204,9 @@ int adamw_launch(const MfacMlpDims* dims, float* params, const float* grads, flo
   if (!params || !grads || !mu || !nu) return MFAC_ERR_NULL;
   if (count < 0) return MFAC_ERR_BAD_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
-  mfac::AdamArgs a;
-  a.p = params; a.g = grads; a.mu = mu; a.nu = nu;
-  a.sw = reinterpret_cast<__nv_bfloat16*>(shadow);
-  a.sb = shadow ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(shadow) + d.bias_section_bytes_offset) : nullptr;
-  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = weight_decay; a.gscale = grad_scale;
-  const double c = (double)count + 1.0;
-  a.inv_bc1 = (float)(1.0 / (1.0 - std::pow((double)b1, c)));
-  a.inv_bc2 = (float)(1.0 / (1.0 - std::pow((double)b2, c)));
-  a.bc_dev = nullptr;
-  if (count_dev) {
-    mfac::adamw_bias_correction_kernel<<<1, 1, 0, s>>>(count_dev, scratch_dev, b1, b2);
-    mfac::count_launch();
-    a.bc_dev = scratch_dev;
-  }
-  const int64_t threads = mfac::ceil_div<int64_t>(d.total, 4);
-  // 16 B read + 12 B write per parameter, + 2 B bf16 shadow
-  void* prof = mfac::profile_begin(MFAC_PROF_ADAMW, (shadow ? 30.0 : 28.0) * (double)d.total, s);
-  mfac::adamw_kernel<<<(unsigned)mfac::ceil_div<int64_t>(threads, 256), 256, 0, s>>>(a, d);
-  mfac::profile_end(prof, s);
-  mfac::count_launch();
-  return mfac::launch_status();
+  mfac::AdamWLaunch h{params, grads, mu, nu, shadow, lr, b1, b2, eps, weight_decay, grad_scale, 0.f, 0.f, nullptr};
+  MFAC_OK(mfac::adamw_prepare(h, count, count_dev, scratch_dev, s, true));
+  return mfac::adamw_segments(d, h, 0, d.total, 0, 1, s);
 }
 }  // namespace
 

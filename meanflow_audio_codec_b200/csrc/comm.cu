@@ -16,6 +16,7 @@ typedef int (*GetUniqueIdFn)(NcclUniqueId*);
 typedef int (*CommInitRankFn)(NcclComm*, int, NcclUniqueId, int);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*CommDestroyFn)(NcclComm);
+typedef int (*GroupFn)(void);
 
 struct Api {
   void* handle = nullptr;
@@ -23,6 +24,7 @@ struct Api {
   CommInitRankFn init_rank = nullptr;
   AllReduceFn all_reduce = nullptr;
   CommDestroyFn destroy = nullptr;
+  GroupFn group_start = nullptr, group_end = nullptr;
 };
 Api g_api;
 NcclComm g_comm = nullptr;
@@ -39,12 +41,30 @@ bool load_api() {
     g_api.init_rank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
     g_api.all_reduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
     g_api.destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
-    if (g_api.get_id && g_api.init_rank && g_api.all_reduce && g_api.destroy) return true;
+    g_api.group_start = (GroupFn)dlsym(h, "ncclGroupStart");
+    g_api.group_end = (GroupFn)dlsym(h, "ncclGroupEnd");
+    if (g_api.get_id && g_api.init_rank && g_api.all_reduce && g_api.destroy && g_api.group_start && g_api.group_end) return true;
   }
   g_api = Api{};
   return false;
 }
 }  // namespace
+
+// ---- internal entry points of the fused training step (imf.cu) ----
+bool comm_ready() { return g_comm != nullptr; }
+// sum all-reduce, in place, of nseg strided fp32 segments [buf + j * stride, + count) as ONE NCCL group (one fused launch)
+int comm_allreduce_segments_f32(float* buf, int64_t count, int64_t stride, int nseg, cudaStream_t stream) {
+  if (!g_comm) return MFAC_ERR_NCCL;
+  if (count <= 0 || nseg <= 0) return MFAC_SUCCESS;
+  if (nseg > 1 && g_api.group_start() != 0) return MFAC_ERR_NCCL;
+  int rc = 0;
+  for (int j = 0; j < nseg && rc == 0; ++j) {
+    float* b = buf + (int64_t)j * stride;
+    rc = g_api.all_reduce(b, b, (size_t)count, 7 /*ncclFloat32*/, 0 /*ncclSum*/, g_comm, stream);
+  }
+  if (nseg > 1 && g_api.group_end() != 0) return MFAC_ERR_NCCL;
+  return rc == 0 ? MFAC_SUCCESS : MFAC_ERR_NCCL;
+}
 }  // namespace mfac
 
 extern "C" {

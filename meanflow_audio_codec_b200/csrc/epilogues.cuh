@@ -69,6 +69,7 @@ struct NoRegs {};
 
 // g = gelu(acc + bias); optionally keeps the pre-activation a (bf16) for the tangent/backward.
 struct EpiBiasGelu {
+  static constexpr bool kNarrowTiles = true;
   static constexpr const char* name = "bias_gelu";
   static constexpr int kPrefetchDepth = 1;
   static constexpr bool kTmaStore = false;
@@ -91,6 +92,7 @@ struct EpiBiasGelu {
 };
 // out = acc * gelu'(a)   (tangent through GELU, and the backward of GELU)
 struct EpiMulDgelu {
+  static constexpr bool kNarrowTiles = true;
   static constexpr const char* name = "mul_dgelu";
   static constexpr int kPrefetchDepth = 2;
   static constexpr bool kTmaStore = false;
@@ -133,6 +135,7 @@ struct EpiMulDgeluColsum : EpiMulDgelu {
 };
 // out = acc (+ bias)
 struct EpiLinearBf16 {
+  static constexpr bool kNarrowTiles = true;
   static constexpr const char* name = "linear_bf16";
   static constexpr int kPrefetchDepth = 1;
   static constexpr bool kTmaStore = false;
@@ -206,6 +209,7 @@ struct EpiAffineResidual {
 };
 // block output: o = acc + b2;  x_new = o (1 + s2) / nb + x_old      (mlp_flow.py:112-117)
 struct EpiBlockOut {
+  static constexpr bool kNarrowTiles = true;
   static constexpr const char* name = "block_out";
   static constexpr int kPrefetchDepth = 2;
   static constexpr bool kTmaStore = false;
@@ -241,6 +245,7 @@ struct EpiBlockOut {
 };
 // tangent of the block output: xd_new = (od (1+s2) + o s2d) / nb + xd_old
 struct EpiBlockOutTangent {
+  static constexpr bool kNarrowTiles = true;
   static constexpr const char* name = "block_out_tangent";
   static constexpr int kPrefetchDepth = 1;
   static constexpr bool kTmaStore = false;

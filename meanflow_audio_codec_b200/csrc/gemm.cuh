@@ -162,6 +162,14 @@ struct epi_colsum : std::false_type {};
 template <class E>
 struct epi_colsum<E, std::void_t<decltype(E::kColSum)>> : std::bool_constant<E::kColSum> {};
 
+// Functors with Epi::kNarrowTiles also get a 64-column tile instantiation: GEMMs of a few hundred rows are bound by what ONE
+// SM can pull from L2 (a 128 x 128 x K tile reads 2 x 128 x K operand elements), so the chain GEMMs of the small-batch step
+// spread over twice as many SMs with half the B operand each.
+template <class E, class = void>
+struct epi_narrow : std::false_type {};
+template <class E>
+struct epi_narrow<E, std::void_t<decltype(E::kNarrowTiles)>> : std::bool_constant<E::kNarrowTiles> {};
+
 // One epilogue warp's share of one output tile: 32 rows (its TMEM lane quarter) x every other 32-column chunk.
 // FULL = the tile lies entirely inside the matrix (no row / column predicates in the hot loop).
 // The functor's global operands are fetched (coalesced) TWO chunks ahead into two register sets: the first two
@@ -808,7 +816,7 @@ int launch_gemm_bn(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, in
 // still sees ONE stream-ordered operation.  Streams and events are created once per (thread, device); forks are plain
 // event record / wait pairs, which stream capture turns into graph edges (GraphedTrainStep replays them as a DAG).
 struct ForkCtx {
-  static constexpr int kStreams = 3;
+  static constexpr int kStreams = 6;
   static constexpr int kEvents = 1024;
   cudaStream_t side[kStreams];
   cudaEvent_t ev[kEvents];
@@ -825,6 +833,7 @@ inline int stream_after(ForkCtx* fc, cudaStream_t from, cudaStream_t to) {
   return MFAC_SUCCESS;
 }
 
+void phase_mark(int id, cudaStream_t s);   // runtime.cu: debug event at a phase boundary (no-op unless mfac_debug_phase_marks(1))
 bool pair_gemm_enabled();   // runtime.cu: on unless MFAC_NO_PAIR_GEMM is set / mfac_debug_set_pair_gemm(0)
 bool stream_k_enabled();    // runtime.cu: on unless MFAC_NO_STREAM_K is set
 
@@ -951,6 +960,11 @@ int launch_gemm(const GemmOperandDesc& A, const GemmOperandDesc& B, int M, int N
   }
   if constexpr (!Epi::kTmaStore) {
     if (!force_bn && pair_gemm_enabled() && pair_gemm_pays(M, N, K, split_k)) return launch_gemm_pair<A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, split_k);
+  }
+  if constexpr (epi_narrow<Epi>::value && !Epi::kTmaStore) {
+    // small M: the 128-wide tiling leaves most SMs idle and each busy one L2-bandwidth bound -> 64-wide tiles
+    if (!force_bn && !split_k && N % 64 == 0 && ceil_div(M, GEMM_BM) * ceil_div(N, 128) * 4 <= num_sms())
+      return launch_gemm_bn<64, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, 1);
   }
   if (bn == 256) return launch_gemm_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);
   return launch_gemm_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, epi, stream, splits);

@@ -121,12 +121,35 @@ inline bool concurrent_rows(int64_t B) { return concurrency_max_rows() > 0 && B 
 // Scratch of one (unsaved) forward evaluation.
 struct FwdScratch {
   __nv_bfloat16 *gc, *m, *hin, *g;
-  void plan(Arena& ar, const Dims& d, int64_t B) {
+  int64_t m_blk_stride = 0;   // > 0: one modulation buffer per block (m + k * m_blk_stride) -- the hoisted schedule
+  void plan(Arena& ar, const Dims& d, int64_t B, bool per_block_m = false) {
     gc = ar.take<__nv_bfloat16>(B * d.Ca);   // first modulation layer of all blocks: [B, nb*Cp]
-    m = ar.take<__nv_bfloat16>(B * d.Mp);
+    m_blk_stride = per_block_m ? B * d.Mp : 0;
+    m = ar.take<__nv_bfloat16>(B * d.Mp * (per_block_m ? d.nb : 1));
     hin = ar.take<__nv_bfloat16>(B * d.Ip);
     g = ar.take<__nv_bfloat16>(B * d.Ip);
   }
+};
+
+// The second modulation layer of a block depends on the conditioning only, not on the residual stream: in the concurrent
+// schedule all blocks' modulation GEMMs of a pass leave the block chain for a side stream (`sm`) right after the batched
+// first layer, and block k waits for event k.
+struct Hoist {
+  ForkCtx* fc = nullptr;
+  cudaStream_t sm = nullptr;
+  cudaEvent_t ev[64];
+  bool on() const { return fc != nullptr; }
+  template <class Fn>
+  int run(cudaStream_t st, int nb, Fn&& fn) {
+    MFAC_OK(stream_after(fc, st, sm));
+    for (int k = 0; k < nb; ++k) {
+      MFAC_OK(fn(k, sm));
+      ev[k] = fc->next_event();
+      MFAC_CUDA_OK(cudaEventRecord(ev[k], sm));
+    }
+    return MFAC_SUCCESS;
+  }
+  int wait(cudaStream_t st, int k) const { return cuda_status(cudaStreamWaitEvent(st, ev[k], 0)); }
 };
 
 // x <- f(x, cond, lat) in place over all blocks (no activations kept).
@@ -134,22 +157,30 @@ struct FwdScratch {
 // modulation MLP then runs on a single row and its output is broadcast (row stride 0) instead of being
 // materialised as a [B, 2I+D] tensor -- 7 KB per row per block less HBM traffic and one large GEMM less.
 int forward_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* cond, const float* lat, float* x, int64_t B,
-                 const FwdScratch& sc, cudaStream_t s, bool uniform_cond = false) {
+                 const FwdScratch& sc, cudaStream_t s, bool uniform_cond = false, Hoist* hz = nullptr) {
   const int M = (int)B;
   const int Mc = uniform_cond ? 1 : M;
   const int64_t m_stride = uniform_cond ? 0 : d.Mp;
   const float inv_nb = 1.0f / (float)d.nb;
+  const bool hoist = hz && hz->on() && sc.m_blk_stride > 0;
   // first modulation layer of ALL blocks in one GEMM (they share the input row `cond`)
   MFAC_OK(gemm_bias_gelu(cond, d.Cp, sh.w + d.s_c1all, Mc, d.Ca, d.Cp, sh.b + d.b_c1all, sc.gc, nullptr, d.Ca, s));
+  auto mod = [&](int k, cudaStream_t st) -> int {
+    return gemm_linear_bf16(sc.gc + k * d.Cp, d.Ca, sh.w + k * d.s_blk_stride + d.s_c2w, Mc, d.Mp, d.Cp,
+                            sh.b + k * d.b_blk_stride + d.b_c2, sc.m + (hoist ? k * sc.m_blk_stride : 0), d.Mp, st);
+  };
+  if (hoist) MFAC_OK(hz->run(s, d.nb, mod));
   for (int k = 0; k < d.nb; ++k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     const float* bias = sh.b + k * d.b_blk_stride;
-    MFAC_OK(gemm_linear_bf16(sc.gc + k * d.Cp, d.Ca, w + d.s_c2w, Mc, d.Mp, d.Cp, bias + d.b_c2, sc.m, d.Mp, s));
-    LnModArgs la{lat, x, sc.m, sc.hin, nullptr, nullptr, nullptr, nullptr, nullptr, m_stride};
+    const __nv_bfloat16* m = sc.m + (hoist ? k * sc.m_blk_stride : 0);
+    if (hoist) MFAC_OK(hz->wait(s, k));
+    else MFAC_OK(mod(k, s));
+    LnModArgs la{lat, x, m, sc.hin, nullptr, nullptr, nullptr, nullptr, nullptr, m_stride};
     MFAC_OK(lnmod(false, la, d, B, s));
     MFAC_OK(gemm_bias_gelu(sc.hin, d.Ip, w + d.s_m1w, M, d.Ip, d.Ip, bias + d.b_m1, sc.g, nullptr, d.Ip, s));
     MFAC_OK(gemm_fwd(sc.g, d.Ip, w + d.s_m2w, M, d.Dp, d.Ip,
-                     EpiBlockOut{bias + d.b_m2, sc.m, x, x, nullptr, m_stride, d.Dp, 2 * d.Ip, inv_nb}, s));
+                     EpiBlockOut{bias + d.b_m2, m, x, x, nullptr, m_stride, d.Dp, 2 * d.Ip, inv_nb}, s));
   }
   return MFAC_SUCCESS;
 }
@@ -166,8 +197,9 @@ int encoder_pass(const Dims& d, const Shadow& sh, const __nv_bfloat16* xb, __nv_
 int colsum(const __nv_bfloat16* G, int ld, int64_t B, float* out, int kind, int limit, const Dims& d, cudaStream_t s,
            int ncols = 0) {
   if (ncols == 0) ncols = ld;
-  const int R = (int)ceil_div<int64_t>(B, COLSUM_VROWS);
-  launch_pdl(colsum_atomic_vec_kernel, dim3(ceil_div(ncols, 256), R), dim3(256), 0, s, G, ld, ncols, B, out, kind, limit, d);
+  const int vrows = colsum_vrows(B);
+  const int R = (int)ceil_div<int64_t>(B, vrows);
+  launch_pdl(colsum_atomic_vec_kernel, dim3(ceil_div(ncols, 256), R), dim3(256), 0, s, G, ld, ncols, B, out, kind, limit, d, vrows);
   count_launch();
   return launch_status();
 }
@@ -193,6 +225,7 @@ struct LossGradPlan {
   SavedBlock blk[64];
   // tangent transients
   __nv_bfloat16 *gcd, *md, *hind, *gd;   // gcd: [B, nb*Cp]
+  int64_t md_blk_stride = 0;             // > 0: one tangent-modulation buffer per block (hoisted schedule)
   __nv_bfloat16 *ac_all, *gc_all;        // [B, nb*Cp]: pre-activation / activation of the batched first modulation layer
   float* xd;
   // loss / backward
@@ -212,7 +245,7 @@ struct LossGradPlan {
     g_e = ar.take<__nv_bfloat16>(B * d.Hep);
     lat = ar.take<float>(B * d.Lp);
     v = ar.take<float>(B * d.Dp);
-    fs.plan(ar, d, B);
+    fs.plan(ar, d, B, concurrent_rows(B));
     xs = ar.take<float>((int64_t)(d.nb + 1) * B * d.Dp);
     ac_all = ar.take<__nv_bfloat16>(B * d.Ca);
     gc_all = ar.take<__nv_bfloat16>(B * d.Ca);
@@ -229,7 +262,8 @@ struct LossGradPlan {
       sb.rstd = ar.take<float>(B);
     }
     gcd = ar.take<__nv_bfloat16>(B * d.Ca);
-    md = ar.take<__nv_bfloat16>(B * d.Mp);
+    md_blk_stride = concurrent_rows(B) ? B * d.Mp : 0;
+    md = ar.take<__nv_bfloat16>(B * d.Mp * (md_blk_stride ? d.nb : 1));
     hind = ar.take<__nv_bfloat16>(B * d.Ip);
     gd = ar.take<__nv_bfloat16>(B * d.Ip);
     xd = ar.take<float>(B * d.Dp);
@@ -352,10 +386,23 @@ int mfac_mlp_forward(const MfacMlpDims* dims, const float* params, const void* s
   return launch_status();
 }
 
-int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
-                       const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
-                       const MfacImfAux* aux, int64_t B, void* ws, size_t ws_bytes, void* stream) {
-  (void)params;
+}  // extern "C"
+
+namespace mfac {
+// Internal notification of the fused training step: grads[off, off + cnt) (nseg strided repetitions) will receive no further
+// contribution once everything enqueued on `st` so far has run.  Block k's slice minus its first modulation layer is final
+// right after block k's backward; the first-modulation-layer slices of all blocks (batched into one GEMM) and the encoder
+// follow at the end.
+struct SliceHook {
+  virtual int final(int64_t off, int64_t cnt, int64_t stride, int nseg, cudaStream_t st) = 0;
+  virtual ~SliceHook() = default;
+};
+bool comm_ready();
+int comm_allreduce_segments_f32(float* buf, int64_t count, int64_t stride, int nseg, cudaStream_t stream);
+
+static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, const void* shadow, const float* x, const float* e,
+                          const float* t, const float* r, float* loss, float* grads, const MfacImfAux* aux, int64_t B, void* ws,
+                          size_t ws_bytes, void* stream, SliceHook* hook) {
   sweep_reset();
   Dims d;
   MFAC_OK(make_dims(dims, &d));
@@ -399,10 +446,12 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   // with e - x
   PrepArgs pa{x, e, t, r, p.e, need_v && (!share || conc_fwd) ? p.v : nullptr, p.xs, cfg->method == MFAC_LOSS_MEAN_FLOW ? p.v : nullptr,
               p.xb, p.t, p.r, need_v ? p.cond_v : nullptr, p.cond_u, p.dcond_u, *cfg, B};
+  phase_mark(0, s);
   launch_pdl(imf_prep_kernel, dim3((unsigned)B), dim3(ROW_THREADS), 0, s, pa, d);
   count_launch();
   // ---- latents = encode(x)
   MFAC_OK(encoder_pass(d, sh, p.xb, p.a_e, p.g_e, p.lat, B, s));
+  phase_mark(1, s);
   // one block of the saved primal pass over rows [r0, r0 + rows): activations go to the per-block buffers the tangent
   // pass and the backward read
   auto primal_mod = [&](int k, int64_t r0, int rows, cudaStream_t st) -> int {
@@ -424,12 +473,14 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
                     EpiBlockOut{bias + d.b_m2, sb.m + r0 * d.Mp, x_in, x_out, sb.o + r0 * d.Dp, d.Mp, d.Dp, 2 * d.Ip, inv_nb, keep}, st);
   };
   // the saved primal pass (all blocks) over rows [r0, r0 + rows) with conditioning rows `cond`
-  auto saved_pass = [&](const __nv_bfloat16* cond, int64_t r0, int rows, int keep, cudaStream_t st) -> int {
+  auto saved_pass = [&](const __nv_bfloat16* cond, int64_t r0, int rows, int keep, cudaStream_t st, Hoist* hz) -> int {
     MFAC_OK(gemm_bias_gelu(cond + r0 * d.Cp, d.Cp, sh.w + d.s_c1all, rows, d.Ca, d.Cp, sh.b + d.b_c1all, p.gc_all + r0 * d.Ca,
                            p.ac_all + r0 * d.Ca, d.Ca, st));
+    if (hz) MFAC_OK(hz->run(st, d.nb, [&](int k, cudaStream_t sm) { return primal_mod(k, r0, rows, sm); }));
     for (int k = 0; k < d.nb; ++k) {
       SavedBlock& sb = p.blk[k];
-      MFAC_OK(primal_mod(k, r0, rows, st));
+      if (hz) MFAC_OK(hz->wait(st, k));
+      else MFAC_OK(primal_mod(k, r0, rows, st));
       LnModArgs la{p.lat + r0 * d.Lp, p.xs + (int64_t)k * B * d.Dp + r0 * d.Dp, sb.m + r0 * d.Mp, sb.hin + r0 * d.Ip, nullptr, nullptr,
                    nullptr, sb.mu + r0, sb.rstd + r0, d.Mp};
       MFAC_OK(lnmod(false, la, d, rows, st));
@@ -438,46 +489,61 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     return MFAC_SUCCESS;
   };
   // one block of the tangent pass over rows [h, B); with_primal: the fused AdaLN kernel also produces the primal's hin / statistics
-  auto tangent_block = [&](int k, bool with_primal, cudaStream_t st) -> int {
+  // tangent of block k's modulation (no bias: d/dt of a constant)
+  auto tangent_mod = [&](int k, cudaStream_t st) -> int {
+    return gemm_linear_bf16(p.gcd + h * d.Ca + k * d.Cp, d.Ca, sh.w + k * d.s_blk_stride + d.s_c2w, Mu, d.Mp, d.Cp, nullptr,
+                            p.md + k * p.md_blk_stride + h * d.Mp, d.Mp, st);
+  };
+  auto tangent_block = [&](int k, bool with_primal, cudaStream_t st, Hoist* hz) -> int {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     SavedBlock& sb = p.blk[k];
     float* x_in = p.xs + (int64_t)k * B * d.Dp + h * d.Dp;
     const float* xd_in = (k == 0 ? p.v : p.xd) + h * d.Dp;
-    MFAC_OK(gemm_linear_bf16(p.gcd + h * d.Ca + k * d.Cp, d.Ca, w + d.s_c2w, Mu, d.Mp, d.Cp, nullptr, p.md + h * d.Mp, d.Mp, st));
-    LnModArgs la{p.lat + h * d.Lp, x_in, sb.m + h * d.Mp, with_primal ? sb.hin + h * d.Ip : nullptr, xd_in, p.md + h * d.Mp,
+    const __nv_bfloat16* md = p.md + k * p.md_blk_stride + h * d.Mp;
+    if (hz) MFAC_OK(hz->wait(st, k));
+    else MFAC_OK(tangent_mod(k, st));
+    LnModArgs la{p.lat + h * d.Lp, x_in, sb.m + h * d.Mp, with_primal ? sb.hin + h * d.Ip : nullptr, xd_in, md,
                  p.hind + h * d.Ip, with_primal ? sb.mu + h : nullptr, with_primal ? sb.rstd + h : nullptr, d.Mp};
     MFAC_OK(lnmod(true, la, d, Mu, st));
     // the tangent GEMMs read the primal pre-activation a and block output o: primal first
     if (with_primal) MFAC_OK(primal_mlp(k, h, Mu, Mu, st));
     MFAC_OK(gemm_fwd(p.hind + h * d.Ip, d.Ip, w + d.s_m1w, Mu, d.Ip, d.Ip, EpiMulDgelu{sb.a + h * d.Ip, p.gd + h * d.Ip, d.Ip}, st));
     return gemm_fwd(p.gd + h * d.Ip, d.Ip, w + d.s_m2w, Mu, d.Dp, d.Ip,
-                    EpiBlockOutTangent{sb.m + h * d.Mp, p.md + h * d.Mp, sb.o + h * d.Dp, xd_in, p.xd + h * d.Dp, d.Mp, d.Dp,
+                    EpiBlockOutTangent{sb.m + h * d.Mp, md, sb.o + h * d.Dp, xd_in, p.xd + h * d.Dp, d.Mp, d.Dp,
                                        2 * d.Ip, inv_nb}, st);
   };
   if (conc_fwd) {
     // ---- three independent forward chains side by side, then the tangent chain
     cudaStream_t sV = fc->side[0], sS = fc->side[1];
+    Hoist hzU, hzV, hzS, hzT;   // every chain's modulation GEMMs run ahead of it on a side stream of their own
+    hzU.fc = hzV.fc = hzS.fc = hzT.fc = fc;
+    hzU.sm = hzT.sm = fc->side[3]; hzV.sm = fc->side[4]; hzS.sm = fc->side[5];
     MFAC_OK(stream_after(fc, s, sV));
     MFAC_OK(stream_after(fc, s, sS));
     if (Mu > 0) {   // v = f(z, [t, 0], lat) on the rows with r != t (in place on p.v, nothing kept)
-      MFAC_OK(forward_pass(d, sh, p.cond_v + h * d.Cp, p.lat + h * d.Lp, p.v + h * d.Dp, Mu, p.fs, sV));
-      MFAC_OK(saved_pass(p.cond_u, h, Mu, Mu, s));
-      if (tangent)
+      MFAC_OK(forward_pass(d, sh, p.cond_v + h * d.Cp, p.lat + h * d.Lp, p.v + h * d.Dp, Mu, p.fs, sV, false, &hzV));
+      MFAC_OK(saved_pass(p.cond_u, h, Mu, Mu, s, &hzU));
+      if (tangent) {
+        // tangent of the first modulation layer (needs the primal's pre-activation ac_all, which side[3] already waits for) and
+        // the tangent modulation GEMMs of all blocks, behind the primal's modulation GEMMs on the same side stream
         MFAC_OK(gemm_fwd(p.dcond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp,
-                         EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, s));
+                         EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, hzT.sm));
+        MFAC_OK(hzT.run(hzT.sm, d.nb, tangent_mod));
+      }
     }
-    if (h > 0) MFAC_OK(saved_pass(p.cond_v, 0, (int)h, (int)h, sS));   // rows with r == t: u IS v
+    if (h > 0) MFAC_OK(saved_pass(p.cond_v, 0, (int)h, (int)h, sS, &hzS));   // rows with r == t: u IS v
     MFAC_OK(stream_after(fc, sV, s));
     MFAC_OK(stream_after(fc, sS, s));
     if (h > 0 && aux && aux->v)
       MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.xs + (int64_t)d.nb * B * d.Dp, (size_t)h * d.Dp * 4, cudaMemcpyDeviceToDevice, s));
-    for (int k = 0; k < d.nb && Mu > 0 && tangent; ++k) MFAC_OK(tangent_block(k, false, s));
+    phase_mark(2, s);
+    for (int k = 0; k < d.nb && Mu > 0 && tangent; ++k) MFAC_OK(tangent_block(k, false, s, &hzT));
   } else {
   // ---- v = f(z, [t, 0], lat)
   if (share) {
     // saved primal pass over ALL rows with the (t, 0) conditioning: v for every row, and already u (with every
     // activation the tangent pass and the backward need) for rows [0, h)
-    MFAC_OK(saved_pass(p.cond_v, 0, M, (int)h, s));   // rows [h, B) get their a / o from the u pass below
+    MFAC_OK(saved_pass(p.cond_v, 0, M, (int)h, s, nullptr));   // rows [h, B) get their a / o from the u pass below
     // v is the tangent seed of the rows that still get a u pass (and an optional test output for all rows)
     const int64_t v0 = (aux && aux->v) ? 0 : h;
     if (v0 < B)
@@ -501,7 +567,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   for (int k = 0; k < d.nb && Mu > 0; ++k) {
     if (tangent) {
       MFAC_OK(primal_mod(k, h, Mu, s));
-      MFAC_OK(tangent_block(k, true, s));
+      MFAC_OK(tangent_block(k, true, s, nullptr));
     } else {
       SavedBlock& sb = p.blk[k];
       MFAC_OK(primal_mod(k, h, Mu, s));
@@ -514,6 +580,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   }
   if (h > 0 && tangent && aux && aux->dudt) MFAC_CUDA_OK(cudaMemsetAsync(p.xd, 0, (size_t)h * d.Dp * 4, s));  // reported as 0
   const float* u = p.xs + (int64_t)d.nb * B * d.Dp;
+  phase_mark(3, s);
   // ---- loss and its seed gradient
   LossArgs lo{u, tangent ? p.xd : nullptr, p.e, x, p.t, p.r, p.g_x, p.row_loss, aux ? aux->per_example : nullptr, *cfg, B};
   launch_pdl(imf_loss_kernel, dim3((unsigned)B), dim3(ROW_THREADS), (size_t)d.Dp * 4, s, lo, d);
@@ -523,6 +590,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   // ---- backward through the primal u rows (weight gradients accumulate split-K partials atomically)
   MFAC_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)d.total * 4, s));
   MFAC_CUDA_OK(cudaMemsetAsync(p.g_lat, 0, (size_t)B * d.Lp * 4, s));
+  phase_mark(4, s);
   // Concurrent schedule: the critical chain (block-output backward -> two dX GEMMs -> LayerNorm backward) stays on `s`; the
   // weight gradients, the remaining bias column sums and the modulation-MLP input gradient of block k run on a side stream from
   // transient set k & 1, which the critical chain only overwrites again two blocks later (after that block's side work).
@@ -539,9 +607,10 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     __nv_bfloat16* g_m = par ? p.g_m2 : p.g_m;
     if (conc && side_done[par]) MFAC_CUDA_OK(cudaStreamWaitEvent(s, side_done[par], 0));   // set `par` is free again
     // g_o, g_s2 and both of their bias-gradient column sums (db2, the s2 third of dbc2) in one pass
-    launch_pdl(bwd_block_out_vec_kernel, dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, COLSUM_VROWS)), dim3(256), 0, s,
+    const int vrows = colsum_vrows(B);
+    launch_pdl(bwd_block_out_vec_kernel, dim3(ceil_div(d.Dp, 256), (unsigned)ceil_div<int64_t>(B, vrows)), dim3(256), 0, s,
                (const float*)p.g_x, (const __nv_bfloat16*)sb.m, (const __nv_bfloat16*)sb.o, g_o, g_m, gk + d.o_m2b, gk + d.o_c2b, d, B,
-               sweep_next());
+               sweep_next(), vrows);
     count_launch();
     if (conc) MFAC_OK(stream_after(fc, s, sW));
     MFAC_OK(gemm_dw(sb.g, d.Ip, g_o, d.Dp, d.Ip, d.Dp, M, EpiGradStore{gk + d.o_m2w, d.D, MAP_CM, 0, MAP_ID, d.D, 1, d}, sW));
@@ -568,6 +637,7 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     }
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
+    phase_mark(5 + (d.nb - 1 - k), s);
     if (conc) MFAC_OK(stream_after(fc, s, sW));
     MFAC_OK(gemm_dw(sb.gc, d.Ca, g_m, d.Mp, d.Cp, d.Mp, M,
                     EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, sW));
@@ -578,6 +648,8 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
       side_done[par] = fc->next_event();
       MFAC_CUDA_OK(cudaEventRecord(side_done[par], sW));
     }
+    // block k's slice (all of it but the first modulation layer) is final once the side work above has run
+    if (hook) MFAC_OK(hook->final((int64_t)k * d.blk_stride + d.o_c2b, d.blk_stride - d.o_c2b, 0, 1, sW));
     if (k == 0) {
       if (conc) MFAC_OK(stream_after(fc, sW, s));   // every block's side work (in order on sW) is done
       // first modulation layer, all blocks at once: dW = cond^T @ g_ac_all, db = column sums
@@ -598,6 +670,11 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   MFAC_OK(colsum(p.g_ae, d.Hep, B, grads + d.o_e1b, MAP_ID, d.He, d, s));
   if (aux && aux->grad_ready)
     aux->grad_ready(aux->grad_ready_user, (int64_t)d.nb * d.blk_stride, d.total - (int64_t)d.nb * d.blk_stride);
+  phase_mark(90, s);
+  if (hook) {   // the nb first-modulation-layer slices [k * stride, + o_c2b) and the encoder
+    MFAC_OK(hook->final(0, d.o_c2b, d.blk_stride, d.nb, s));
+    MFAC_OK(hook->final((int64_t)d.nb * d.blk_stride, d.total - (int64_t)d.nb * d.blk_stride, 0, 1, s));
+  }
   // ---- optional intermediates for parity tests
   if (aux) {
     const unsigned nbk = blocks_for(B * d.D, 256);
@@ -609,6 +686,62 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
     if (aux->r) MFAC_CUDA_OK(cudaMemcpyAsync(aux->r, p.r, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
   }
   return launch_status();
+}
+}  // namespace mfac
+
+extern "C" {
+
+int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
+                       const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
+                       const MfacImfAux* aux, int64_t B, void* ws, size_t ws_bytes, void* stream) {
+  (void)params;
+  return loss_grad_impl(dims, cfg, shadow, x, e, t, r, loss, grads, aux, B, ws, ws_bytes, stream, nullptr);
+}
+
+namespace {
+// AdamW (and, for world > 1, the gradient all-reduce before it) applied slice by slice as the backward finalises them
+struct TrainHook : SliceHook {
+  Dims d;
+  AdamWLaunch h;
+  float* grads;
+  int world;
+  // Large batches keep the machine busy on their own (single-stream schedule): there the exchange and the update stay ONE
+  // all-reduce and ONE pass over the parameters after the backward (nine smaller collectives on the compute stream only add
+  // latency, and NCCL kernels beside the persistent one-CTA-per-SM GEMMs cost more than the exchange).
+  bool deferred;
+  int final(int64_t off, int64_t cnt, int64_t stride, int nseg, cudaStream_t st) override {
+    if (deferred) {
+      if (off != (int64_t)d.nb * d.blk_stride) return MFAC_SUCCESS;   // the encoder slice is announced last
+      if (world > 1) MFAC_OK(comm_allreduce_segments_f32(grads, d.total, 0, 1, st));
+      return adamw_segments(d, h, 0, d.total, 0, 1, st);
+    }
+    if (world > 1) MFAC_OK(comm_allreduce_segments_f32(grads + off, cnt, stride, nseg, st));
+    return adamw_segments(d, h, off, cnt, stride, nseg, st);
+  }
+};
+}  // namespace
+
+int mfac_imf_train_step(const MfacMlpDims* dims, const MfacImfConfig* cfg, const MfacAdamWConfig* opt, float* params, void* shadow,
+                        float* mu, float* nu, int64_t count, uint64_t* count_dev, float* scratch_dev, const float* x,
+                        const float* e, const float* t, const float* r, float* loss, float* grads, const MfacImfAux* aux,
+                        int64_t B, int32_t world, void* ws, size_t ws_bytes, void* stream) {
+  if (!opt || !params || !shadow || !mu || !nu || !grads) return MFAC_ERR_NULL;
+  if (count < 0 || world < 1) return MFAC_ERR_BAD_SHAPE;
+  if (world > 1 && !comm_ready()) return MFAC_ERR_NCCL;
+  TrainHook hook;
+  MFAC_OK(make_dims(dims, &hook.d));
+  hook.h = AdamWLaunch{params, grads, mu, nu, shadow, opt->lr, opt->b1, opt->b2, opt->eps, opt->weight_decay, 1.0f / (float)world,
+                       0.f, 0.f, nullptr};
+  hook.grads = grads;
+  hook.world = world;
+  hook.deferred = !(concurrent_rows(B) && fork_ctx() != nullptr);
+  // bias correction first (host value, or the device counter read and advanced once per step for graph replay)
+  MFAC_OK(adamw_prepare(hook.h, count, count_dev, scratch_dev, (cudaStream_t)stream, /*advance=*/false));
+  MFAC_OK(loss_grad_impl(dims, cfg, shadow, x, e, t, r, loss, grads, aux, B, ws, ws_bytes, stream, &hook));
+  // the prologue read the counter as the RNG step (MfacImfConfig.step_dev may be the same word): advance it last
+  if (count_dev) MFAC_OK(adamw_advance(count_dev, (cudaStream_t)stream));
+  phase_mark(99, (cudaStream_t)stream);
+  return MFAC_SUCCESS;
 }
 
 int mfac_sample(const MfacMlpDims* dims, const float* params, const void* shadow, const float* latents, const float* noise,

@@ -423,6 +423,13 @@ __global__ void f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t
 
 // padded -> real column maps of the flat (Flax-order) gradient
 constexpr int COLSUM_VROWS = 256;
+// rows per CTA slab of the column-sum style kernels: 256 for large batches (few atomics), down to 8 for small ones so that a
+// 128-row batch still spreads over dozens of CTAs instead of one per 256 columns
+inline int colsum_vrows(int64_t B) {
+  int v = COLSUM_VROWS;
+  while (v > 8 && B / v < 64) v >>= 1;
+  return v;
+}
 enum ColMap { MAP_ID = 0, MAP_CM = 1, MAP_MM = 2, MAP_C1ALL = 3 };
 __device__ __forceinline__ int map_col(int kind, int p, int limit, const Dims& d) {
   if (kind == MAP_CM) return d.cm_inv(p);
@@ -636,13 +643,13 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
 // grid (Dp/256, ceil(B/256)); thread = 8 columns x every 8th row of a 256-row slab (same shape as the column-sum kernel).
 __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x, const __nv_bfloat16* m, const __nv_bfloat16* o,
                                                                 __nv_bfloat16* g_o, __nv_bfloat16* g_m, float* db_o, float* db_m,
-                                                                Dims d, int64_t B, int reverse) {
+                                                                Dims d, int64_t B, int reverse, int vrows) {
   MFAC_PDL_SYNC();
   __shared__ float s_red[2][8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
-  const int64_t r0 = (int64_t)(reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y) * COLSUM_VROWS;
-  const int64_t r1 = min(B, r0 + COLSUM_VROWS);
+  const int64_t r0 = (int64_t)(reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y) * vrows;
+  const int64_t r1 = min(B, r0 + vrows);
   const float inv_nb = 1.0f / (float)d.nb;
   float so[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < d.Dp) {
@@ -682,13 +689,13 @@ __global__ void __launch_bounds__(256) bwd_block_out_vec_kernel(const float* g_x
 // the slab's sums are added to out[map(col)] with red.global.add (out is zeroed with the rest of the gradient, like the
 // split-K weight gradients it sits next to).
 __global__ void __launch_bounds__(256) colsum_atomic_vec_kernel(const __nv_bfloat16* G, int ld, int ncols, int64_t B, float* out,
-                                                                int kind, int limit, Dims d) {
+                                                                int kind, int limit, Dims d, int vrows) {
   MFAC_PDL_SYNC();
   __shared__ float s_red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
-  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_VROWS;
-  const int64_t r1 = min(B, r0 + COLSUM_VROWS);
+  const int64_t r0 = (int64_t)blockIdx.y * vrows;
+  const int64_t r1 = min(B, r0 + vrows);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < ncols) {
 #pragma unroll 2

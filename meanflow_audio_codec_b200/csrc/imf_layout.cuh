@@ -163,6 +163,24 @@ __host__ __device__ inline ShadowSlot shadow_slot_of(const Dims& d, int64_t i) {
   return {d.s_e2w + (int64_t)r * d.Lp + c, false};
 }
 
+// Fused AdamW (adamw.cu), launchable over slices of the flat parameter vector
+struct AdamWLaunch {
+  float* params;
+  const float* grads;
+  float* mu;
+  float* nu;
+  void* shadow;              // may be null
+  float lr, b1, b2, eps, weight_decay, grad_scale;
+  float inv_bc1, inv_bc2;    // filled by adamw_prepare
+  const float* bc_dev;       // device copy of the two factors (graph replay) or null
+};
+// advance = false leaves the device counter untouched (the fused step's prologue still has to read it as the RNG step;
+// adamw_advance increments it once the step's launches are enqueued)
+int adamw_prepare(AdamWLaunch& h, int64_t count, uint64_t* count_dev, float* scratch_dev, cudaStream_t s, bool advance);
+int adamw_advance(uint64_t* count_dev, cudaStream_t s);
+int adamw_segments(const Dims& d, const AdamWLaunch& h, int64_t seg_off, int64_t seg_cnt, int64_t seg_stride, int nseg,
+                   cudaStream_t s);
+
 // Simple bump allocator over the caller-provided workspace (256-byte aligned slices).
 struct Arena {
   uint8_t* base;

@@ -64,6 +64,21 @@ void profile_end(void* token, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   cudaEventRecord(g_prof[reinterpret_cast<size_t>(token) - 1].e1, s);
 }
+// ---- phase marks (debug): events at the phase boundaries of one mfac_imf_loss_grad / train_step call
+namespace {
+std::atomic<int> g_phase_on{0};
+std::mutex g_phase_mu;
+std::vector<std::pair<int, cudaEvent_t>> g_phase;
+}  // namespace
+void phase_mark(int id, cudaStream_t s) {
+  if (!g_phase_on.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  std::lock_guard<std::mutex> lock(g_phase_mu);
+  g_phase.push_back({id, e});
+}
+
 bool simt_gemm_enabled() { return g_simt.load(std::memory_order_relaxed) != 0; }
 bool pair_gemm_enabled() { return g_pair.load(std::memory_order_relaxed) != 0; }
 bool stream_k_enabled() { return g_streamk.load(std::memory_order_relaxed) != 0; }
@@ -214,6 +229,32 @@ int mfac_profile_collect(int64_t* launches, double* ms, double* work) {
   if (csv) fclose(csv);
   g_prof.clear();
   return MFAC_SUCCESS;
+}
+
+int mfac_debug_phase_marks(int32_t on) {
+  mfac::g_phase_on.store(on ? 1 : 0);
+  return MFAC_SUCCESS;
+}
+
+// ids[i], ms_since_first[i] of the marks recorded so far (cleared afterwards); returns the number of marks
+int mfac_debug_phase_collect(int32_t* ids, float* ms_since_first, int32_t cap) {
+  using namespace mfac;
+  if (!ids || !ms_since_first) return MFAC_ERR_NULL;
+  if (cudaDeviceSynchronize() != cudaSuccess) return MFAC_ERR_DRIVER;
+  std::lock_guard<std::mutex> lock(g_phase_mu);
+  int n = 0;
+  for (auto& pr : g_phase) {
+    if (n < cap) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, g_phase[0].second, pr.second);
+      ids[n] = pr.first;
+      ms_since_first[n] = t;
+      ++n;
+    }
+  }
+  for (auto& pr : g_phase) cudaEventDestroy(pr.second);
+  g_phase.clear();
+  return n;
 }
 
 int mfac_debug_counters(int64_t* kernel_launches) {

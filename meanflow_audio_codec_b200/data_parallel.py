@@ -33,6 +33,28 @@ class DataParallel:
             else:
                 dist.init_process_group(backend, rank=self.rank, world_size=self.world)
 
+        self.fused = False
+
+    def init_library_comm(self) -> bool:
+        """Second NCCL communicator owned by libmfac (``mfac_comm_init``): the fused training step issues the gradient
+        all-reduce itself, slice by slice, on the stream each slice becomes final on.  The 128-byte NCCL id is made by
+        rank 0 and broadcast over ``torch.distributed``.  Returns False (and leaves the torch path in charge) on CPU / gloo."""
+        if not self.enabled or not torch.cuda.is_available() or dist.get_backend() != "nccl":
+            return False
+        import ctypes as C
+
+        from . import _lib
+        buf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.check(_lib.lib().mfac_comm_unique_id(buf), "comm_unique_id")
+        idt = torch.tensor(list(buf), dtype=torch.uint8, device=torch.device("cuda", self.local_rank))
+        dist.broadcast(idt, src=0)
+        raw = (C.c_ubyte * 128)(*idt.cpu().tolist())
+        with torch.cuda.device(self.local_rank):
+            _lib.check(_lib.lib().mfac_comm_init(raw, self.rank, self.world), "comm_init")
+        self.fused = True
+        return True
+
     # ------------------------------------------------------------ sharding
     def shard_rows(self, n: int) -> tuple[int, int]:
         """[start, stop) of this rank's rows of a global batch of n (n must divide evenly: the
@@ -64,6 +86,10 @@ class DataParallel:
         return float(t.item())
 
     def destroy(self):
+        if self.fused:
+            from . import _lib
+            _lib.lib().mfac_comm_destroy()
+            self.fused = False
         if self.enabled and dist.is_initialized():
             dist.destroy_process_group()
 
@@ -73,6 +99,10 @@ def train_step_dp(dp: DataParallel, state, key, x_local, loss_strategy, **kw):
     grad_scale = 1/world.  The RNG rows are offset by rank so shards draw independent (e, t, r); the
     "first half gets r = t" rule (utils.py:41-44) is applied per local shard."""
     kw.setdefault("row_offset", dp.rank * x_local.shape[0])
+    if (not dp.enabled or getattr(dp, "fused", False)) and hasattr(loss_strategy, "train_step_fused") and hasattr(state, "tx"):
+        # ONE library call: loss/grad schedule, per-slice NCCL all-reduce over libmfac's own communicator (world > 1) and AdamW
+        state, loss, _ = loss_strategy.train_step_fused(state, key, x_local, world=dp.world if dp.enabled else 1, **kw)
+        return state, loss, key
     if not dp.enabled:
         loss, grads = loss_strategy.compute_loss(state, key, x_local, **kw)
     elif os.environ.get("MFAC_DP_OVERLAP", "0") != "1":

@@ -60,6 +60,10 @@ class GraphedTrainStep:
         if self.tok is not None:
             x = self.tok.tokenize(x)
             x = x.reshape(x.shape[0], -1)
+        if hasattr(self.strategy, "train_step_fused"):
+            _, loss, _ = self.strategy.train_step_fused(self.state, self.key, x, step_tensor=self.count, count_tensor=self.count,
+                                                        scratch=self.scratch)
+            return loss
         loss, grads = self.strategy.compute_loss(self.state, self.key, x, step_tensor=self.count)
         self.state.apply_gradients(grads=grads, count_tensor=self.count, scratch=self.scratch)
         return loss

@@ -108,7 +108,7 @@ class _FusedLossStrategy(LossStrategy):
 
     def compute_loss(self, state: TrainState, key, x, *, noise=None, t=None, r=None, step: int | None = None,
                      row_offset: int = 0, return_aux: bool = False, step_tensor=None, grad_ready=None,
-                     rows_r_equals_t: int = 0):
+                     rows_r_equals_t: int = 0, _train: dict | None = None):
         """``rows_r_equals_t``: with explicit ``t``/``r``, a promise that the first so many rows have r == t (the rule
         ``sample_tr`` applies, utils.py:41-44) -- their u pass then doubles as their v pass; -1 disables that sharing for the
         internal draws too.  ``step_tensor``: optional uint64 CUDA scalar read on the device as the RNG step (CUDA-graph replay).
@@ -149,17 +149,41 @@ class _FusedLossStrategy(LossStrategy):
         ws = model.workspace(_lib.WS_LOSS_GRAD, B, dev)
         ptr = lambda a: None if a is None else a.data_ptr()  # noqa: E731
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().mfac_imf_loss_grad(
-                C.byref(model.dims), C.byref(cfg), fp.flat.data_ptr(), fp.shadow().data_ptr(), x.data_ptr(),
-                ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
-                C.byref(aux) if aux is not None else None, B, ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
-                "imf_loss_grad")
+            if _train is None:
+                _lib.check(_lib.lib().mfac_imf_loss_grad(
+                    C.byref(model.dims), C.byref(cfg), fp.flat.data_ptr(), fp.shadow().data_ptr(), x.data_ptr(),
+                    ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
+                    C.byref(aux) if aux is not None else None, B, ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+                    "imf_loss_grad")
+            else:
+                # fused step: the same schedule with AdamW (and, for world > 1, the all-reduce) applied slice by slice
+                tx = state.tx
+                opt = _lib.AdamWConfig(tx.learning_rate, tx.b1, tx.b2, tx.eps, tx.weight_decay)
+                ct, sc = _train.get("count_tensor"), _train.get("scratch")
+                _lib.check(_lib.lib().mfac_imf_train_step(
+                    C.byref(model.dims), C.byref(cfg), C.byref(opt), fp.flat.data_ptr(), fp.shadow().data_ptr(),
+                    state.opt_state["mu"].data_ptr(), state.opt_state["nu"].data_ptr(), int(state.opt_state["count"]),
+                    ptr(ct), ptr(sc), x.data_ptr(), ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
+                    C.byref(aux) if aux is not None else None, B, int(_train.get("world", 1)), ws.data_ptr(), ws.numel(),
+                    _lib.stream_ptr()), "imf_train_step")
+                fp.mark_shadow_current()
         self.last_aux = aux_t if return_aux else None
         from .mlp_flow import FlatParams
         gtree = FlatParams(model, grads).tree()
         if return_aux:
             return loss, gtree, aux_t
         return loss, gtree
+
+
+    def train_step_fused(self, state: TrainState, key, x, *, world: int = 1, count_tensor=None, scratch=None, **kw):
+        """``mfac_imf_train_step``: loss, gradients and the AdamW update in ONE call (the update of each block's slice is
+        enqueued as soon as the backward has finalised it).  ``world > 1`` sum-all-reduces every slice over the
+        ``mfac_comm`` communicator first and scales by 1 / world.  Returns (new_state, loss, grads)."""
+        out = self.compute_loss(state, key, x, _train=dict(world=world, count_tensor=count_tensor, scratch=scratch), **kw)
+        if count_tensor is None:
+            state.opt_state["count"] += 1
+            state = TrainState(state.step + 1, state.apply_fn, state.params, state.tx, state.opt_state, state.model)
+        return (state,) + tuple(out)
 
 
 class ImprovedMeanFlowLoss(_FusedLossStrategy):
@@ -257,6 +281,9 @@ def train_step(state: TrainState, key, x, loss_strategy: LossStrategy | None = N
     """(state, loss, key) -- trainers/training_steps.py:37-61.  The key is returned unchanged, as in the reference."""
     if loss_strategy is None:
         loss_strategy = FlowMatchingLoss()   # the reference's default (training_steps.py:58-59)
+    if isinstance(loss_strategy, _FusedLossStrategy) and isinstance(state, TrainState):
+        state, loss, _ = loss_strategy.train_step_fused(state, key, x, **kw)
+        return state, loss, key
     loss, grads = loss_strategy.compute_loss(state, key, x, **kw)
     state = state.apply_gradients(grads=grads)
     return state, loss, key
