@@ -318,7 +318,8 @@ def run_mfac(args):
         params = model.init(CFG["seed"], device=dev, on_device=Dm > 2048)["params"]
         state = m.TrainState.create(apply_fn=model.apply, params=params, tx=m.adamw(CFG["base_lr"], CFG["weight_decay"]))
         strat = m.ImprovedMeanFlowLoss(m.LinearNoiseSchedule(0.001, 0.999), m.MeanFlowTimeSampling(-0.4, 1.0, 0.5), True)
-        tok = m.MDCTTokenization(window_size=CFG["window_size"], hop_size=CFG["hop_size"])
+        # lazy: the step tokenises inside its own prologue (mfac_imf_train_step_audio) -- no [B, nf, N] token tensor in HBM
+        tok = m.MDCTTokenization(window_size=CFG["window_size"], hop_size=CFG["hop_size"], lazy=os.environ.get("MFAC_BENCH_EAGER_TOKENS") != "1")
         g = torch.Generator(device=dev).manual_seed(42 + rank)
         x_raw = 0.1 * torch.randn(B, Tm, device=dev, generator=g)
         return model, state, strat, tok, x_raw
@@ -379,31 +380,13 @@ def run_mfac(args):
     # Input pipeline: two pinned host batches, uploaded on a copy stream into two device buffers so that the upload of
     # step i+1 overlaps the compute of step i; the loss is read back to the host every step.
     x_host = [x_raw.cpu().pin_memory(), x_raw.flip(0).cpu().pin_memory()]
-    x_dev = [torch.empty_like(x_raw), torch.empty_like(x_raw)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def upload(i):
-        b = i & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])           # the step that last read this buffer has finished
-            x_dev[b].copy_(x_host[b], non_blocking=True)
-            ready[b].record(copy_stream)
+    stager = m.HostBatchStager(device=dev)     # the package's input pipeline (input_pipeline.py)
 
     def e2e_loop(n):
         nonlocal state
-        for b in range(2):
-            consumed[b].record(torch.cuda.current_stream())
-        upload(0)
         lv = None
-        for i in range(n):
-            b = i & 1
-            torch.cuda.current_stream().wait_event(ready[b])
-            if i + 1 < n:
-                upload(i + 1)
-            state, loss = step_fn(state, strat, tok, x_dev[b])
-            consumed[b].record(torch.cuda.current_stream())
+        for x_d in stager.stream(x_host[i & 1] for i in range(n)):
+            state, loss = step_fn(state, strat, tok, x_d)
             lv = float(loss)  # device -> host read every step, like trainers/train.py:347
         return lv
 
@@ -415,8 +398,8 @@ def run_mfac(args):
     e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
     dp.barrier()
     e2e = {"value": B * world * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(x_host[0].numel() * 4),
-           "d2h_bytes_per_step": 4, "api": "MDCTTokenization.tokenize + train_step (ImprovedMeanFlowLoss); pinned host audio, "
-           "double-buffered upload on a copy stream, loss read back every step"}
+           "d2h_bytes_per_step": 4, "api": "HostBatchStager.stream (pinned host audio, double-buffered upload on a copy stream) -> "
+           "MDCTTokenization(lazy).tokenize -> train_step (ImprovedMeanFlowLoss, fused mfac_imf_train_step_audio); loss read back every step"}
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM): per-launch CUDA events on the launch stream
     roofline, families = None, None

@@ -201,6 +201,20 @@ MFAC_API int mfac_imf_train_step(const MfacMlpDims* dims, const MfacImfConfig* c
                         const float* x, const float* e, const float* t, const float* r, float* loss, float* grads,
                         const MfacImfAux* aux, int64_t B, int32_t world, void* ws, size_t ws_bytes, void* stream);
 
+/* Raw-audio forms (the hot loop tokenises and steps back to back, trainers/train.py:339-345):
+ * audio[B, T] fp32 takes the place of x[B, D]; each clip's MDCT tokens (window_size, hop_size; direct cosine branch) are one
+ * model row, nf * window_size == D.  For window 512 / hop 256 and up to 16 frames per row the tokeniser's store stage IS the
+ * step's prologue -- no token tensor is written to HBM; other geometries tokenise into scratch first (same results). */
+MFAC_API int mfac_imf_loss_grad_audio(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
+                             const float* audio, int64_t T, int32_t window_size, int32_t hop_size, const float* e, const float* t,
+                             const float* r, float* loss, float* grads, const MfacImfAux* aux, int64_t B, void* ws,
+                             size_t ws_bytes, void* stream);
+MFAC_API int mfac_imf_train_step_audio(const MfacMlpDims* dims, const MfacImfConfig* cfg, const MfacAdamWConfig* opt, float* params,
+                              void* shadow, float* mu, float* nu, int64_t count, uint64_t* count_dev, float* scratch_dev,
+                              const float* audio, int64_t T, int32_t window_size, int32_t hop_size, const float* e, const float* t,
+                              const float* r, float* loss, float* grads, const MfacImfAux* aux, int64_t B, int32_t world, void* ws,
+                              size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ samplers
  * MFAC_SAMPLE_HEUN  ref: evaluators/sampling.py:5-95 (h = 0, grid linspace(1,0,n), dt = 1/n).
  * MFAC_SAMPLE_MF    mean-flow few-step rule x_r = x_t - (t-r) u(x_t,[t,t-r]) on a uniform grid

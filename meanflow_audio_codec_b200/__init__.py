@@ -17,3 +17,4 @@ from .graphs import GraphedTrainStep  # noqa: F401
 from .flows import ConditionalConvFlow, ConditionalMLPMixerFlow, create_flow_model  # noqa: F401
 from .checkpoint import load_checkpoint, save_checkpoint  # noqa: F401
 from .codec import MeanFlowCodec  # noqa: F401
+from .input_pipeline import HostBatchStager, LazyTokens  # noqa: F401

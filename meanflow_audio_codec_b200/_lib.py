@@ -101,6 +101,11 @@ PROTOTYPES = {
                                      C.POINTER(ImfAux), _I64, _P, C.c_size_t, _P]),
     "mfac_imf_train_step": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), C.POINTER(AdamWConfig), _P, _P, _P, _P, _I64, _P, _P,
                                       _P, _P, _P, _P, _P, _P, C.POINTER(ImfAux), _I64, _I32, _P, C.c_size_t, _P]),
+    "mfac_imf_loss_grad_audio": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P,
+                                           C.POINTER(ImfAux), _I64, _P, C.c_size_t, _P]),
+    "mfac_imf_train_step_audio": (C.c_int, [C.POINTER(MlpDims), C.POINTER(ImfConfig), C.POINTER(AdamWConfig), _P, _P, _P, _P, _I64, _P,
+                                            _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, C.POINTER(ImfAux), _I64, _I32, _P,
+                                            C.c_size_t, _P]),
     "mfac_adamw_step": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_adamw_step_dev": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _P]),
     "mfac_sample": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _I32, _I32, _F, C.c_uint64, _P, _I64, _P,

@@ -11,38 +11,12 @@
 #pragma once
 
 #include "imf_layout.cuh"
+#include "imf_prep.cuh"
 #include "epilogues.cuh"
 
 namespace mfac {
 
 constexpr int ROW_THREADS = 256;
-
-// ---------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG (own stream; the reference's threefry stream is not imitated,
-// parity runs pass e/t/r explicitly -- SURVEY.md R6)
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
-// 4 x N(0,1) for counter (idx, stream, step)
-__device__ __forceinline__ float4 philox_normal4(uint64_t idx, uint32_t stream, uint64_t seed, uint64_t step) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), stream ^ (uint32_t)(step << 8), (uint32_t)(step >> 24)),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
-  float s0, c0, s1, c1;
-  sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
-  sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
-}
 
 __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
   v = warp_sum(v);
@@ -59,45 +33,9 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
   return red[0];
 }
 
-// cond[j] = cos(t f_j) + cos(h f_j), cond[half+j] = sin(t f_j) + sin(h f_j); optional d/ds along (tdot=1,hdot=1)
-__device__ __forceinline__ void write_cond_row(float t, float h, int C, int Cp, __nv_bfloat16* cond, __nv_bfloat16* dcond) {
-  const int half = C / 2;
-  for (int j = threadIdx.x; j < Cp; j += blockDim.x) {
-    float v = 0.f, dv = 0.f;
-    if (j < C) {
-      const int q = j < half ? j : j - half;
-      const float f = expf(-9.210340371976184f * (float)q / (float)half);
-      float st, ct, sh, ch;
-      sincosf(t * f, &st, &ct);
-      sincosf(h * f, &sh, &ch);
-      if (j < half) { v = ct + ch; dv = -f * (st + sh); }
-      else { v = st + sh; dv = f * (ct + ch); }
-    }
-    cond[j] = __float2bfloat16(v);
-    if (dcond) dcond[j] = __float2bfloat16(dv);
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // iMF prologue: one block per row.  e, t, r drawn or copied; z_t; bf16 copy of x; three cond rows.
 // ---------------------------------------------------------------------------------------
-struct PrepArgs {
-  const float* x;      // [B, D]
-  const float* e_in;   // [B, D] or null
-  const float* t_in;   // [B] or null
-  const float* r_in;   // [B] or null
-  float* e;            // [B, Dp]
-  float* z;            // [B, Dp] or null  z_t for the v pass (improved mean flow only), updated in place by it
-  float* z2;           // [B, Dp]  z_t for the u pass
-  float* seed;         // [B, Dp] or null  tangent seed noise_max e - x (mean flow: the JVP runs along the true velocity)
-  __nv_bfloat16* xb;   // [B, Dp]
-  float* t;            // [B]
-  float* r;            // [B]
-  __nv_bfloat16 *cond_v, *cond_u, *dcond_u;  // [B, Cp]
-  MfacImfConfig cfg;
-  int64_t B;
-};
-
 __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims d) {
   MFAC_PDL_SYNC();
   const int64_t b = blockIdx.x;
@@ -105,20 +43,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
   __shared__ float s_tr[2];
   if (threadIdx.x == 0) {
     float t, r;
-    if (a.t_in) {
-      t = a.t_in[b];
-      r = a.r_in[b];
-    } else {
-      const float4 n4 = philox_normal4(a.cfg.row_offset + b, 1u, a.cfg.seed, step);
-      float lt = 1.0f / (1.0f + expf(-(n4.x * a.cfg.time_std + a.cfg.time_mean)));
-      const float lr = 1.0f / (1.0f + expf(-(n4.y * a.cfg.time_std + a.cfg.time_mean)));
-      if (a.cfg.uniform_time) lt = 0.5f * (1.0f + erff(n4.x * 0.70710678118654752f));  // Phi(N(0,1)) ~ U(0,1)
-      t = fmaxf(lt, lr);
-      r = fminf(lt, lr);
-      if (b < (int64_t)((float)a.B * a.cfg.data_proportion)) r = t;  // utils.py:41-44, per local shard
-      if (a.cfg.method == MFAC_LOSS_FLOW_MATCHING) t = lt;           // a single time (time_sampling.py:44-75)
-    }
-    if (a.cfg.method == MFAC_LOSS_FLOW_MATCHING) r = t;               // h = 0 (loss_strategies.py:88)
+    draw_tr(a, b, step, t, r);
     s_tr[0] = t; s_tr[1] = r;
     a.t[b] = t; a.r[b] = r;
   }
@@ -138,14 +63,16 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
       const float4 xv = *reinterpret_cast<const float4*>(a.x + at);
       const float4 e = a.e_in ? *reinterpret_cast<const float4*>(a.e_in + at) : make_float4(ev[0], ev[1], ev[2], ev[3]);
       const float omt = 1.0f - t;
-      const float4 zt = make_float4(omt * xv.x + nscale * e.x, omt * xv.y + nscale * e.y, omt * xv.z + nscale * e.z,
-                                    omt * xv.w + nscale * e.w);
-      *reinterpret_cast<float4*>(a.e + at) = e;
+      const float4 zt = make_float4(zt_of(omt, xv.x, nscale, e.x), zt_of(omt, xv.y, nscale, e.y), zt_of(omt, xv.z, nscale, e.z),
+                                    zt_of(omt, xv.w, nscale, e.w));
+      if (a.e) *reinterpret_cast<float4*>(a.e + at) = e;
       if (a.z) *reinterpret_cast<float4*>(a.z + at) = zt;
       *reinterpret_cast<float4*>(a.z2 + at) = zt;
-      if (a.seed)
-        *reinterpret_cast<float4*>(a.seed + at) = make_float4(a.cfg.noise_max * e.x - xv.x, a.cfg.noise_max * e.y - xv.y,
-                                                              a.cfg.noise_max * e.z - xv.z, a.cfg.noise_max * e.w - xv.w);
+      const float nmax = a.cfg.noise_max;
+      const float4 tg = make_float4(target_of(nmax, e.x, xv.x), target_of(nmax, e.y, xv.y), target_of(nmax, e.z, xv.z),
+                                    target_of(nmax, e.w, xv.w));
+      *reinterpret_cast<float4*>(a.target + at) = tg;
+      if (a.seed) *reinterpret_cast<float4*>(a.seed + at) = tg;
       *reinterpret_cast<uint2*>(a.xb + at) = make_uint2(pack_bf16(xv.x, xv.y), pack_bf16(xv.z, xv.w));
       continue;
     }
@@ -157,11 +84,12 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_prep_kernel(PrepArgs a, Dims 
         xv = a.x[b * d.D + j];
         e = a.e_in ? a.e_in[b * d.D + j] : ev[q];
       }
-      a.e[b * d.Dp + j] = e;
-      const float zt = (1.0f - t) * xv + nscale * e;
+      if (a.e) a.e[b * d.Dp + j] = e;
+      const float zt = zt_of(1.0f - t, xv, nscale, e);
       if (a.z) a.z[b * d.Dp + j] = zt;
       a.z2[b * d.Dp + j] = zt;
-      if (a.seed) a.seed[b * d.Dp + j] = a.cfg.noise_max * e - xv;
+      a.target[b * d.Dp + j] = target_of(a.cfg.noise_max, e, xv);
+      if (a.seed) a.seed[b * d.Dp + j] = target_of(a.cfg.noise_max, e, xv);
       a.xb[b * d.Dp + j] = __float2bfloat16(xv);
     }
   }
@@ -279,8 +207,7 @@ __global__ void __launch_bounds__(ROW_THREADS) lnmod_kernel(LnModArgs a, Dims d)
 //       g_u = 2 w_b delta / B   (weighted)   or   2 delta / (B D)   (plain MSE)
 // ---------------------------------------------------------------------------------------
 struct LossArgs {
-  const float *u, *dudt, *e;  // [B, Dp]
-  const float* x;             // [B, D]
+  const float *u, *dudt, *target;  // [B, Dp]; target = noise_max e - x, written by the prologue
   const float *t, *r;         // [B]
   float* g_x;                 // [B, Dp]
   float* row_loss;            // [B]
@@ -309,9 +236,8 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
         const float4 dd = *reinterpret_cast<const float4*>(a.dudt + i);
         vp.x += tr * dd.x; vp.y += tr * dd.y; vp.z += tr * dd.z; vp.w += tr * dd.w;
       }
-      const float4 e = *reinterpret_cast<const float4*>(a.e + i), xv = *reinterpret_cast<const float4*>(a.x + i);
-      const float4 dl = make_float4(vp.x - (a.cfg.noise_max * e.x - xv.x), vp.y - (a.cfg.noise_max * e.y - xv.y),
-                                    vp.z - (a.cfg.noise_max * e.z - xv.z), vp.w - (a.cfg.noise_max * e.w - xv.w));
+      const float4 tg = *reinterpret_cast<const float4*>(a.target + i);
+      const float4 dl = make_float4(vp.x - tg.x, vp.y - tg.y, vp.z - tg.z, vp.w - tg.w);
       *reinterpret_cast<float4*>(s_delta + j) = dl;
       sq += dl.x * dl.x + dl.y * dl.y + dl.z * dl.z + dl.w * dl.w;
     }
@@ -321,7 +247,7 @@ __global__ void __launch_bounds__(ROW_THREADS) imf_loss_kernel(LossArgs a, Dims 
       if (j < d.D) {
         const int64_t i = b * d.Dp + j;
         const float vpred = use_dudt ? a.u[i] + tr * a.dudt[i] : a.u[i];
-        dl = vpred - (a.cfg.noise_max * a.e[i] - a.x[b * d.D + j]);
+        dl = vpred - a.target[i];
       }
       s_delta[j] = dl;
       sq += dl * dl;

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "mfac_common.cuh"
+#include "imf_prep.cuh"   // prologue of the iMF step (PrepArgs, draw_tr, Philox, cond rows) for the fused tokenise + prologue kernel
 
 namespace mfac {
 
@@ -609,6 +610,143 @@ mdct512h256_short_kernel(const float* __restrict__ x, float* __restrict__ X, Fft
   }
 }
 
+
+// ------------------------------------------------------------------ fused tokenise + iMF prologue
+// The training loop tokenises a batch and hands the tokens to the loss (trainers/train.py:339-345).  For short clips
+// (nf <= 16 frames per row: the 784- / 2048- / 4096-sample rows of the benchmarks) this kernel is the short-clip MDCT above
+// with the iMF prologue (imf_prep_kernel) as its store stage: a coefficient pair never goes to HBM as a token -- it leaves the
+// registers as z_t, as the loss target noise_max e - x, and as the encoder's bf16 input row.  (e, t, r) are the same draws
+// imf_prep_kernel makes for the same (seed, step, row): the noise quad of four consecutive columns is computed by one lane of
+// an even / odd lane pair and shared with a shuffle.
+__global__ void __launch_bounds__(F2_THREADS, 2)
+tokenize_prep_short_kernel(const float* __restrict__ x, FftTables tab, int64_t T, int nf, int cpc, int64_t x_clip_stride,
+                           PrepArgs a, Dims d) {
+  MFAC_PDL_SYNC();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int need = (nf - 1) * FFT_H + 2 * FFT_N;     // samples a clip's frames touch
+  const int pw = need / 2 / 128 * 144;               // skewed words per plane per clip
+  float* sE = reinterpret_cast<float*>(smem_raw);
+  float* sO = sE + cpc * pw;
+  float2* sEx = reinterpret_cast<float2*>(sO + cpc * pw);
+  float2* sPost = sEx + (F2_THREADS / 16) * F2_EX;
+  __shared__ float s_t[32], s_r[32];
+  const int tid = threadIdx.x, ln = tid & 15, hw = tid >> 4;
+  const int64_t B = a.B;
+  const int64_t b0 = (int64_t)blockIdx.x * cpc;
+  const int nclips = (int)min((int64_t)cpc, B - b0);
+  const int nframes = nclips * nf;
+  const int per_clip4 = need / 4;
+  const int total4 = nclips * per_clip4;
+  const uint64_t step = a.cfg.step_dev ? *a.cfg.step_dev : a.cfg.step;
+  if (tid < nclips) {
+    float t, r;
+    draw_tr(a, b0 + tid, step, t, r);
+    s_t[tid] = t; s_r[tid] = r;
+    a.t[b0 + tid] = t; a.r[b0 + tid] = r;
+  }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((x_clip_stride & 3) == 0);
+  constexpr int BATCH = 10;
+  for (int g0 = 0; g0 < total4; g0 += BATCH * F2_THREADS) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int g = g0 + tid + u * F2_THREADS;
+      const int cl = g / per_clip4, i4 = (g - cl * per_clip4) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < total4) {
+        const float* src = x + (b0 + cl) * x_clip_stride + i4;
+        if (aligned && i4 + 3 < T) v[u] = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (i4 < T) v[u].x = __ldg(src);
+          if (i4 + 1 < T) v[u].y = __ldg(src + 1);
+          if (i4 + 2 < T) v[u].z = __ldg(src + 2);
+          if (i4 + 3 < T) v[u].w = __ldg(src + 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int g = g0 + tid + u * F2_THREADS;
+      if (g < total4) {
+        const int cl = g / per_clip4, q = (g - cl * per_clip4) * 2;
+        const int ph = cl * pw + q + 16 * (q >> 7);
+        *reinterpret_cast<float2*>(sE + ph) = make_float2(v[u].x, v[u].z);
+        *reinterpret_cast<float2*>(sO + ph) = make_float2(v[u].y, v[u].w);
+      }
+    }
+  }
+  float kf[16][4];
+  float2 tw[16];
+  load_fold_constants(tab, kf, tw, ln);
+  sPost[tid] = tab.post[tid];
+  sPost[tid + 128] = tab.post[tid + 128];
+  __syncthreads();
+  // conditioning rows of this CTA's clips (every thread takes part in each row)
+  for (int cl = 0; cl < nclips; ++cl) {
+    const float t = s_t[cl], r = s_r[cl];
+    if (a.cond_v) write_cond_row(t, 0.f, d.C, d.Cp, a.cond_v + (b0 + cl) * d.Cp, nullptr);
+    write_cond_row(t, t - r, d.C, d.Cp, a.cond_u + (b0 + cl) * d.Cp, a.dcond_u + (b0 + cl) * d.Cp);
+  }
+
+  float2* ex = sEx + hw * F2_EX;
+  const int n_it = (nframes + F2_THREADS / 16 - 1) / (F2_THREADS / 16);
+  const bool odd = (ln & 1) != 0;
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it) {
+    const int sl = it * (F2_THREADS / 16) + hw;
+    const int sc = sl < nframes ? sl : nframes - 1;
+    const int cl = sc / nf, fr = sc - cl * nf;
+    float2 c[16];
+    fold_frame(sE + cl * pw + fr * 144, sO + cl * pw + fr * 144, kf, c, ln);
+    fft256_lanes16(c, tw, ex, PostSmem{sPost + ln}, ln);
+    const int64_t b = b0 + cl;
+    const float t = s_t[cl];
+    const float omt = 1.0f - t, nscale = a.cfg.noise_min + a.cfg.noise_max * t, nmax = a.cfg.noise_max;
+    const int64_t row = b * d.Dp + (int64_t)fr * FFT_N + 2 * ln;     // + 32 k2: this lane's coefficient pair k2
+    // tokens X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2
+#pragma unroll
+    for (int kp = 0; kp < 16; kp += 2) {
+      float2 xv[2], ev[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k2 = kp + u;
+        const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
+        xv[u] = make_float2(c[fidx(k2)].x, -im);
+      }
+      if (a.e_in) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) ev[u] = *reinterpret_cast<const float2*>(a.e_in + row + 32 * (kp + u));
+      } else {
+        // noise quad of columns [4 q, 4 q + 4) = this lane pair's two coefficient pairs of k2: the even lane draws the quad of
+        // k2 = kp, the odd lane the quad of k2 = kp + 1; each keeps its half and hands the other half to its neighbour
+        const int k2m = kp + (odd ? 1 : 0);
+        const uint64_t col4 = (uint64_t)((int64_t)fr * FFT_N + 32 * k2m + 2 * (ln & ~1));
+        const uint64_t idx = ((a.cfg.row_offset + (uint64_t)b) * (uint64_t)d.Dp + col4) >> 2;
+        const float4 n4 = philox_normal4(idx, 0u, a.cfg.seed, step);
+        const float2 keep = odd ? make_float2(n4.z, n4.w) : make_float2(n4.x, n4.y);
+        const float2 give = odd ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w);
+        const float gx = __shfl_xor_sync(0xffffffffu, give.x, 1), gy = __shfl_xor_sync(0xffffffffu, give.y, 1);
+        ev[odd ? 1 : 0] = keep;
+        ev[odd ? 0 : 1] = make_float2(gx, gy);
+      }
+      if (sl < nframes) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int64_t at = row + 32 * (kp + u);
+          const float2 zt = make_float2(zt_of(omt, xv[u].x, nscale, ev[u].x), zt_of(omt, xv[u].y, nscale, ev[u].y));
+          const float2 tg = make_float2(target_of(nmax, ev[u].x, xv[u].x), target_of(nmax, ev[u].y, xv[u].y));
+          if (a.e) *reinterpret_cast<float2*>(a.e + at) = ev[u];
+          if (a.z) *reinterpret_cast<float2*>(a.z + at) = zt;
+          *reinterpret_cast<float2*>(a.z2 + at) = zt;
+          *reinterpret_cast<float2*>(a.target + at) = tg;
+          if (a.seed) *reinterpret_cast<float2*>(a.seed + at) = tg;
+          *reinterpret_cast<uint32_t*>(a.xb + at) = pack_bf16(xv[u].x, xv[u].y);
+        }
+      }
+    }
+  }
+}
+
 // inverse: CTA = clip b, output blocks [q0, q0 + I2_BLOCKS) of 256 samples; phase 1 DCT-IV of the <= 32 frames that
 // touch them into shared memory, phase 2 unfold + window + overlap-add as a float4 gather (4 frames per sample).
 __global__ void __launch_bounds__(F2_THREADS, 2)
@@ -1017,6 +1155,34 @@ int mdct_inverse(const float* X, float* y, StridedIO io, int64_t B, int64_t nf, 
   return launch_status();
 }
 
+
+// Fused tokenise + prologue launch (imf.cu).  MFAC_ERR_UNSUPPORTED when the geometry is outside the short-clip kernel: the
+// caller then tokenises into a scratch buffer and runs the plain prologue.
+int tokenize_prep_launch(const float* audio, int64_t T, int N, int hop, const PrepArgs& pa, const Dims& d, cudaStream_t stream) {
+  if (!audio) return MFAC_ERR_NULL;
+  if (N != FFT_N || hop != FFT_H || T <= 0) return MFAC_ERR_UNSUPPORTED;
+  const int64_t nf = T < N ? 1 : (T - N) / hop + 1;
+  if (nf > F2_FRAMES / 2 || nf * N != d.D || d.D != d.Dp) return MFAC_ERR_UNSUPPORTED;
+  if (pa.e_in && (reinterpret_cast<uintptr_t>(pa.e_in) & 7)) return MFAC_ERR_UNSUPPORTED;
+  static const bool off = getenv("MFAC_NO_FUSED_TOKENIZE") != nullptr;
+  if (off) return MFAC_ERR_UNSUPPORTED;
+  TableSet ts;
+  MFAC_OK(get_tables(N, true, &ts));
+  const int cpc = F2_FRAMES / (int)nf;
+  const int need = ((int)nf - 1) * FFT_H + 2 * FFT_N;
+  const size_t smem_s = (size_t)2 * cpc * (need / 2 / 128 * 144) * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    MFAC_CUDA_OK(cudaFuncSetAttribute(tokenize_prep_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured.done();
+  }
+  void* prof = profile_begin(MFAC_PROF_MDCT, 4.0 * (double)pa.B * ((double)T + (double)nf * N), stream);
+  tokenize_prep_short_kernel<<<(unsigned)ceil_div<int64_t>(pa.B, cpc), F2_THREADS, smem_s, stream>>>(audio, ts.fft, T, (int)nf, cpc, T,
+                                                                                                    pa, d);
+  profile_end(prof, stream);
+  count_launch();
+  return launch_status();
+}
 }  // namespace mfac
 
 // ------------------------------------------------------------------ C ABI

@@ -117,7 +117,15 @@ class _FusedLossStrategy(LossStrategy):
         bucket's all-reduce from it."""
         model: ConditionalFlow = state.model
         fp = model.flat_params(state.params)
-        x = _lib.require_cuda(x, "x").to(torch.float32).contiguous()
+        from .input_pipeline import LazyTokens
+        audio = None
+        if isinstance(x, LazyTokens):
+            if x.ndim == 2 and x.shape[1] == model.noise_dimension:
+                audio = x            # the step tokenises in its own prologue (mfac_imf_*_audio)
+            else:
+                x = x.materialize()
+        if audio is None:
+            x = _lib.require_cuda(x, "x").to(torch.float32).contiguous()
         if x.ndim != 2 or x.shape[1] != model.noise_dimension:
             raise ValueError(f"x must be [B, {model.noise_dimension}], got {tuple(x.shape)}")
         B = x.shape[0]
@@ -149,23 +157,26 @@ class _FusedLossStrategy(LossStrategy):
         ws = model.workspace(_lib.WS_LOSS_GRAD, B, dev)
         ptr = lambda a: None if a is None else a.data_ptr()  # noqa: E731
         with torch.cuda.device(dev):
+            xin = ([audio.audio.data_ptr(), int(audio.audio.shape[1]), audio.window_size, audio.hop_size] if audio is not None
+                   else [x.data_ptr()])
+            sfx = "_audio" if audio is not None else ""
             if _train is None:
-                _lib.check(_lib.lib().mfac_imf_loss_grad(
-                    C.byref(model.dims), C.byref(cfg), fp.flat.data_ptr(), fp.shadow().data_ptr(), x.data_ptr(),
+                _lib.check(getattr(_lib.lib(), "mfac_imf_loss_grad" + sfx)(
+                    C.byref(model.dims), C.byref(cfg), fp.flat.data_ptr(), fp.shadow().data_ptr(), *xin,
                     ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
                     C.byref(aux) if aux is not None else None, B, ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
-                    "imf_loss_grad")
+                    "imf_loss_grad" + sfx)
             else:
                 # fused step: the same schedule with AdamW (and, for world > 1, the all-reduce) applied slice by slice
                 tx = state.tx
                 opt = _lib.AdamWConfig(tx.learning_rate, tx.b1, tx.b2, tx.eps, tx.weight_decay)
                 ct, sc = _train.get("count_tensor"), _train.get("scratch")
-                _lib.check(_lib.lib().mfac_imf_train_step(
+                _lib.check(getattr(_lib.lib(), "mfac_imf_train_step" + sfx)(
                     C.byref(model.dims), C.byref(cfg), C.byref(opt), fp.flat.data_ptr(), fp.shadow().data_ptr(),
                     state.opt_state["mu"].data_ptr(), state.opt_state["nu"].data_ptr(), int(state.opt_state["count"]),
-                    ptr(ct), ptr(sc), x.data_ptr(), ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
+                    ptr(ct), ptr(sc), *xin, ptr(noise), ptr(t), ptr(r), loss.data_ptr(), grads.data_ptr(),
                     C.byref(aux) if aux is not None else None, B, int(_train.get("world", 1)), ws.data_ptr(), ws.numel(),
-                    _lib.stream_ptr()), "imf_train_step")
+                    _lib.stream_ptr()), "imf_train_step" + sfx)
                 fp.mark_shadow_current()
         self.last_aux = aux_t if return_aux else None
         from .mlp_flow import FlatParams

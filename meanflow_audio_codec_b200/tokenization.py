@@ -11,11 +11,18 @@ from .mdct import MDCTConfig, imdct, imdct_channels, mdct, mdct_channels, num_fr
 
 
 class MDCTTokenization:
-    def __init__(self, window_size: int = 512, hop_size: int | None = None, config: MDCTConfig | None = None):
+    def __init__(self, window_size: int = 512, hop_size: int | None = None, config: MDCTConfig | None = None,
+                 lazy: bool = False):
+        """``lazy=True``: ``tokenize`` of a mono batch returns ``LazyTokens`` (input_pipeline.py) -- handed to a loss strategy /
+        ``train_step`` the MDCT then runs inside the step's prologue instead of as a separate pass over HBM."""
         self.config = config if config is not None else MDCTConfig(window_size=window_size, hop_size=hop_size)
+        self.lazy = lazy
 
     def tokenize(self, x: torch.Tensor) -> torch.Tensor:
         if x.ndim == 2:
+            if self.lazy:
+                from .input_pipeline import LazyTokens
+                return LazyTokens(x, self.config)
             return mdct(x, config=self.config)
         if x.ndim == 3:
             return mdct_channels(x, self.config.window_size, self.config.hop_size)
