@@ -618,7 +618,7 @@ mdct512h256_short_kernel(const float* __restrict__ x, float* __restrict__ X, Fft
 // registers as z_t, as the loss target noise_max e - x, and as the encoder's bf16 input row.  (e, t, r) are the same draws
 // imf_prep_kernel makes for the same (seed, step, row): the noise quad of four consecutive columns is computed by one lane of
 // an even / odd lane pair and shared with a shuffle.
-__global__ void __launch_bounds__(F2_THREADS, 2)
+__global__ void __launch_bounds__(F2_THREADS, 3)
 tokenize_prep_short_kernel(const float* __restrict__ x, FftTables tab, int64_t T, int nf, int cpc, int64_t x_clip_stride,
                            PrepArgs a, Dims d) {
   MFAC_PDL_SYNC();
@@ -703,15 +703,20 @@ tokenize_prep_short_kernel(const float* __restrict__ x, FftTables tab, int64_t T
     const float t = s_t[cl];
     const float omt = 1.0f - t, nscale = a.cfg.noise_min + a.cfg.noise_max * t, nmax = a.cfg.noise_max;
     const int64_t row = b * d.Dp + (int64_t)fr * FFT_N + 2 * ln;     // + 32 k2: this lane's coefficient pair k2
-    // tokens X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2
+    // tokens X[2k] = Re y_k, X[2k+1] = -Im y_{255-k};  y_{255-k} lives in lane 15 - ln, register 15 - k2.  The spectrum goes
+    // back through the half-warp's exchange buffer so that the store stage is a ROLLED loop (one Philox call, six stores per
+    // trip): unrolled it was 70-100 KB of SASS, far beyond the instruction cache.
+    __syncwarp();
 #pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) ex[k2 * 17 + ln] = c[fidx(k2)];
+    __syncwarp();
+#pragma unroll 1
     for (int kp = 0; kp < 16; kp += 2) {
       float2 xv[2], ev[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int k2 = kp + u;
-        const float im = __shfl_xor_sync(0xffffffffu, c[fidx(15 - k2)].y, 15);
-        xv[u] = make_float2(c[fidx(k2)].x, -im);
+        xv[u] = make_float2(ex[k2 * 17 + ln].x, -ex[(15 - k2) * 17 + (15 - ln)].y);
       }
       if (a.e_in) {
 #pragma unroll
@@ -726,8 +731,8 @@ tokenize_prep_short_kernel(const float* __restrict__ x, FftTables tab, int64_t T
         const float2 keep = odd ? make_float2(n4.z, n4.w) : make_float2(n4.x, n4.y);
         const float2 give = odd ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w);
         const float gx = __shfl_xor_sync(0xffffffffu, give.x, 1), gy = __shfl_xor_sync(0xffffffffu, give.y, 1);
-        ev[odd ? 1 : 0] = keep;
-        ev[odd ? 0 : 1] = make_float2(gx, gy);
+        ev[0] = odd ? make_float2(gx, gy) : keep;
+        ev[1] = odd ? keep : make_float2(gx, gy);
       }
       if (sl < nframes) {
 #pragma unroll
@@ -1168,7 +1173,10 @@ int tokenize_prep_launch(const float* audio, int64_t T, int N, int hop, const Pr
   if (off) return MFAC_ERR_UNSUPPORTED;
   TableSet ts;
   MFAC_OK(get_tables(N, true, &ts));
-  const int cpc = F2_FRAMES / (int)nf;
+  // clips per CTA: at most 16 frame slots (two trips of the 8 half-warps), so that three CTAs fit an SM's shared memory -- the
+  // store stage (Philox + six output streams) wants the occupancy more than the staging wants long segments
+  int cpc = F2_FRAMES / 2 / (int)nf;
+  if (cpc < 1) cpc = 1;
   const int need = ((int)nf - 1) * FFT_H + 2 * FFT_N;
   const size_t smem_s = (size_t)2 * cpc * (need / 2 / 128 * 144) * 4 + (F2_THREADS / 16) * F2_EX * 8 + 256 * 8;
   static PerDeviceOnce configured;
