@@ -746,17 +746,27 @@ struct TrainHook : SliceHook {
   // all-reduce and ONE pass over the parameters after the backward (nine smaller collectives on the compute stream only add
   // latency, and NCCL kernels beside the persistent one-CTA-per-SM GEMMs cost more than the exchange).
   bool deferred;
-  // world > 1, concurrent schedule: consecutive blocks are exchanged as ONE contiguous all-reduce per `bucket_blocks` blocks
-  // (measured on 2 x B200 at 128 rows: one 14 MB collective per block does not reach NVLink bandwidth and the side stream
-  // becomes the critical path: 1.74 ms / step against 1.44 ms for a single 113 MB bucket).  The bucket spans the blocks'
-  // first-modulation-layer regions too -- still zero at that point (their batched GEMM runs last), so summing them early is
-  // harmless; they are exchanged for real, and updated, with the encoder at the end.
+  // world > 1, concurrent schedule: `bucket_blocks` consecutive blocks are exchanged as ONE NCCL group (measured on 2 x B200 at
+  // 128 rows: one 14 MB collective per block does not reach NVLink bandwidth: 1.74 ms / step against 1.44 ms for a single
+  // 113 MB bucket after the backward; two-block buckets on a stream of their own: 1.40 ms).
   int bucket_blocks = 2;
   int pending = 0;
+  // Concurrent schedule: the exchange and the update of a finalised slice run on a stream of their own (side[1], idle during the
+  // backward) behind the stream the slice became final on -- not ON it: that stream carries the weight-gradient GEMMs, and a
+  // collective per bucket in front of them made it the critical path (2 x B200, 128 rows: 1.61 ms against 1.44 ms).
+  ForkCtx* fc = nullptr;
+  cudaStream_t on(cudaStream_t st) {
+    if (!fc) return st;
+    if (stream_after(fc, st, fc->side[1]) != MFAC_SUCCESS) return st;
+    return fc->side[1];
+  }
   int flush(int k_lo, int nblk, cudaStream_t st) {
     if (nblk <= 0) return MFAC_SUCCESS;
-    if (world > 1) MFAC_OK(comm_allreduce_segments_f32(grads + (int64_t)k_lo * d.blk_stride, (int64_t)nblk * d.blk_stride, 0, 1, st));
-    return adamw_segments(d, h, (int64_t)k_lo * d.blk_stride + d.o_c2b, d.blk_stride - d.o_c2b, d.blk_stride, nblk, st);
+    // one NCCL group = one fused launch over the blocks' slices; their first-modulation-layer regions stay out of it (the batched
+    // GEMM that fills them runs later on the main stream and must not race with a collective over the same words)
+    const int64_t off = (int64_t)k_lo * d.blk_stride + d.o_c2b, cnt = d.blk_stride - d.o_c2b;
+    if (world > 1) MFAC_OK(comm_allreduce_segments_f32(grads + off, cnt, d.blk_stride, nblk, st));
+    return adamw_segments(d, h, off, cnt, d.blk_stride, nblk, st);
   }
   int final(int64_t off, int64_t cnt, int64_t stride, int nseg, cudaStream_t st) override {
     if (deferred) {
@@ -768,11 +778,12 @@ struct TrainHook : SliceHook {
       const int k = (int)(off / d.blk_stride);
       ++pending;
       if (pending >= (world > 1 ? bucket_blocks : 1) || k == 0) {
-        MFAC_OK(flush(k, pending, st));
+        MFAC_OK(flush(k, pending, on(st)));
         pending = 0;
       }
       return MFAC_SUCCESS;
     }
+    st = on(st);
     if (world > 1) MFAC_OK(comm_allreduce_segments_f32(grads + off, cnt, stride, nseg, st));
     return adamw_segments(d, h, off, cnt, stride, nseg, st);
   }
@@ -794,10 +805,12 @@ int train_step_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, const Mfa
   hook.grads = grads;
   hook.world = world;
   hook.deferred = !(concurrent_rows(B) && fork_ctx() != nullptr);
+  hook.fc = hook.deferred ? nullptr : fork_ctx();
   if (const char* ev = getenv("MFAC_DP_BUCKET_BLOCKS")) hook.bucket_blocks = atoi(ev) > 0 ? atoi(ev) : 2;
   // bias correction first (host value, or the device counter read and advanced once per step for graph replay)
   MFAC_OK(adamw_prepare(hook.h, count, count_dev, scratch_dev, (cudaStream_t)stream, /*advance=*/false));
   MFAC_OK(loss_grad_impl(dims, cfg, shadow, x, e, t, r, loss, grads, aux, B, ws, ws_bytes, stream, &hook, audio));
+  if (hook.fc) MFAC_OK(stream_after(hook.fc, hook.fc->side[1], (cudaStream_t)stream));   // exchange / update stream rejoins
   // the prologue read the counter as the RNG step (MfacImfConfig.step_dev may be the same word): advance it last
   if (count_dev) MFAC_OK(adamw_advance(count_dev, (cudaStream_t)stream));
   phase_mark(99, (cudaStream_t)stream);

@@ -19,8 +19,10 @@ _SO = Path(__file__).resolve().parent / "libmfac_jax_ffi.so"
 if not _SO.exists():
     raise ImportError(f"{_SO} not built: run `python -m meanflow_audio_codec_b200.jax_ffi.build` on a box with jaxlib")
 _lib = ctypes.CDLL(str(_SO))
-for _name, _sym in (("mfac_mdct", "MfacMdct"), ("mfac_imdct", "MfacImdct"), ("mfac_mlp_forward", "MfacMlpForward"),
-                    ("mfac_imf_loss_grad", "MfacImfLossGrad")):
+TARGETS = (("mfac_mdct", "MfacMdct"), ("mfac_imdct", "MfacImdct"), ("mfac_mlp_forward", "MfacMlpForward"),
+           ("mfac_imf_loss_grad", "MfacImfLossGrad"), ("mfac_mlp_encode", "MfacMlpEncode"), ("mfac_sample", "MfacSample"),
+           ("mfac_mlp_cast_params", "MfacCastParams"), ("mfac_imf_train_step", "MfacImfTrainStep"))
+for _name, _sym in TARGETS:
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_lib, _sym)), platform="CUDA")
 
 
@@ -66,3 +68,20 @@ def imdct(X, window_size: int = 576, hop_size: int | None = None, use_fft_thresh
     out = jax.ffi.ffi_call("mfac_imdct", jax.ShapeDtypeStruct((B, L), jnp.float32))(
         X.reshape(B, nf, N).astype(jnp.float32), window_size=np.int32(N), hop_size=np.int32(hop))
     return out.reshape(*lead, L)
+
+
+def train_step(flat_params, shadow, mu, nu, x, e, t, r, *, dims, count: int, lr: float = 1e-4, weight_decay: float = 1e-4,
+               world: int = 1, workspace_bytes: int):
+    """``train_step`` (trainers/training_steps.py:15-61) as ONE custom call: returns (params', shadow', mu', nu', loss, grads).
+    The four state buffers are donated and updated in place (``input_output_aliases``); ``dims`` = (D, L, C, nb);
+    ``workspace_bytes`` = ``mfac_workspace_bytes(MFAC_WS_LOSS_GRAD, dims, B)`` (ctypes, host side)."""
+    D, L, C, nb = dims
+    P = flat_params.shape[0]
+    outs = (jax.ShapeDtypeStruct(flat_params.shape, jnp.float32), jax.ShapeDtypeStruct(shadow.shape, jnp.uint8),
+            jax.ShapeDtypeStruct(mu.shape, jnp.float32), jax.ShapeDtypeStruct(nu.shape, jnp.float32),
+            jax.ShapeDtypeStruct((), jnp.float32), jax.ShapeDtypeStruct((P,), jnp.float32),
+            jax.ShapeDtypeStruct((workspace_bytes,), jnp.uint8))
+    res = jax.ffi.ffi_call("mfac_imf_train_step", outs, input_output_aliases={0: 0, 1: 1, 2: 2, 3: 3})(
+        flat_params, shadow, mu, nu, x, e, t, r, D=np.int32(D), L=np.int32(L), C=np.int32(C), nb=np.int32(nb),
+        count=np.int64(count), lr=np.float32(lr), weight_decay=np.float32(weight_decay), world=np.int32(world))
+    return res[:6]

@@ -184,3 +184,24 @@ def test_reference_config_file_drives_the_factories():
     assert (strat.time_sampling.mean, strat.time_sampling.std, strat.time_sampling.data_proportion) == (-0.4, 1.0, 0.5)
     opt = m.adamw(cfg.base_lr, cfg.weight_decay)
     assert (opt.learning_rate, opt.weight_decay, opt.b1, opt.b2, opt.eps) == (1e-4, 1e-4, 0.9, 0.999, 1e-8)
+
+
+def test_jax_ffi_handlers_type_check_against_the_c_abi():
+    """The XLA FFI unit cannot be built here (no jaxlib headers), but it can be compiled with -fsyntax-only against a minimal
+    stand-in for xla/ffi/api/ffi.h: every handler body -- above all its call into include/mfac.h -- is type-checked, and each
+    handler's parameter count must match its Ctx/Arg/Ret/Attr chain.  Also: every registered target has a handler symbol."""
+    import re
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    cc = root / "meanflow_audio_codec_b200" / "jax_ffi" / "mfac_jax_ffi.cc"
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the build image"
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", f"-I{root / 'tests' / 'stubs'}",
+                        f"-I{root / 'tests' / 'stubs' / 'cuda'}", f"-I{root / 'include'}", str(cc)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    symbols = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", cc.read_text()))
+    init = (root / "meanflow_audio_codec_b200" / "jax_ffi" / "__init__.py").read_text()
+    registered = set(re.findall(r'\("mfac_\w+", "(\w+)"\)', init))
+    assert registered == symbols and len(symbols) >= 8, (registered, symbols)
