@@ -67,9 +67,20 @@ inline int vec_rows(const Dims& d) {
   return d.Ip / 256;
 }
 
+// wide rows without padded columns: the CTA-per-row vectorised kernels (imf_kernels.cuh)
+inline bool wide_rows(const Dims& d) {
+  return vec_rows(d) == 0 && d.D == d.Dp && d.L == d.Lp && d.Ip <= 8 * 256 * WIDE_MAXV;
+}
+
 int lnmod(bool tangent, const LnModArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
   LnModArgs a = a_in;
-  a.reverse = vec_rows(d) ? sweep_next() : 0;
+  a.reverse = (vec_rows(d) || wide_rows(d)) ? sweep_next() : 0;
+  if (wide_rows(d)) {
+    if (tangent) launch_pdl(lnmod_wide_kernel<true>, dim3((unsigned)B), dim3(256), 0, s, a, d);
+    else launch_pdl(lnmod_wide_kernel<false>, dim3((unsigned)B), dim3(256), 0, s, a, d);
+    count_launch();
+    return launch_status();
+  }
   const size_t smem = (size_t)d.Ip * 4 * (tangent ? 2 : 1);
   if (smem > 200 * 1024) return MFAC_ERR_UNSUPPORTED;
   static PerDeviceOnce configured;
@@ -102,7 +113,12 @@ int lnmod(bool tangent, const LnModArgs& a_in, const Dims& d, int64_t B, cudaStr
 
 int ln_bwd(const LnBwdArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
   LnBwdArgs a = a_in;
-  a.reverse = vec_rows(d) ? sweep_next() : 0;
+  a.reverse = (vec_rows(d) || wide_rows(d)) ? sweep_next() : 0;
+  if (wide_rows(d)) {
+    launch_pdl(ln_bwd_wide_kernel, dim3((unsigned)B), dim3(256), 0, s, a, d);
+    count_launch();
+    return launch_status();
+  }
   const unsigned vgrid = (unsigned)ceil_div<int64_t>(B, 4);   // ~200 registers per thread: 4-row CTAs, two per SM
 #define MFAC_LNBWD_CASE(NVV) case NVV: launch_pdl(ln_bwd_vec_kernel<NVV>, dim3(vgrid), dim3(128), 0, s, a, d, B); break;
   switch (vec_rows(d)) {
@@ -116,7 +132,10 @@ int ln_bwd(const LnBwdArgs& a_in, const Dims& d, int64_t B, cudaStream_t s) {
 }
 
 // Batches this small run the concurrent schedules (independent kernel chains on the library's side streams, gemm.cuh: ForkCtx)
-inline bool concurrent_rows(int64_t B) { return concurrency_max_rows() > 0 && B <= concurrency_max_rows(); }
+// (a batch counts with its width: 4096 rows of D = 1024 are "small", 4096 rows of D = 7680 fill the machine on their own)
+inline bool concurrent_rows(int64_t B, const Dims& d) {
+  return concurrency_max_rows() > 0 && B <= concurrency_max_rows() && B * (int64_t)d.Dp <= (int64_t)concurrency_max_rows() * 1024;
+}
 
 // Scratch of one (unsaved) forward evaluation.
 struct FwdScratch {
@@ -246,7 +265,7 @@ struct LossGradPlan {
     g_e = ar.take<__nv_bfloat16>(B * d.Hep);
     lat = ar.take<float>(B * d.Lp);
     v = ar.take<float>(B * d.Dp);
-    fs.plan(ar, d, B, concurrent_rows(B));
+    fs.plan(ar, d, B, concurrent_rows(B, d));
     xs = ar.take<float>((int64_t)(d.nb + 1) * B * d.Dp);
     ac_all = ar.take<__nv_bfloat16>(B * d.Ca);
     gc_all = ar.take<__nv_bfloat16>(B * d.Ca);
@@ -263,7 +282,7 @@ struct LossGradPlan {
       sb.rstd = ar.take<float>(B);
     }
     gcd = ar.take<__nv_bfloat16>(B * d.Ca);
-    md_blk_stride = concurrent_rows(B) ? B * d.Mp : 0;
+    md_blk_stride = concurrent_rows(B, d) ? B * d.Mp : 0;
     md = ar.take<__nv_bfloat16>(B * d.Mp * (md_blk_stride ? d.nb : 1));
     hind = ar.take<__nv_bfloat16>(B * d.Ip);
     gd = ar.take<__nv_bfloat16>(B * d.Ip);
@@ -278,7 +297,7 @@ struct LossGradPlan {
     g_latb = ar.take<__nv_bfloat16>(B * d.Lp);
     g_ae = ar.take<__nv_bfloat16>(B * d.Hep);
     g_o2 = g_o; g_a2 = g_a; g_m2 = g_m;
-    if (concurrent_rows(B)) {
+    if (concurrent_rows(B, d)) {
       g_o2 = ar.take<__nv_bfloat16>(B * d.Dp);
       g_a2 = ar.take<__nv_bfloat16>(B * d.Ip);
       g_m2 = ar.take<__nv_bfloat16>(B * d.Mp);
@@ -453,7 +472,7 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
   // r == t, the saved primal u pass on the rows with r != t -- and run side by side on the library's side streams; the tangent
   // pass follows on its own (it needs v and the u pass's activations); in the backward the weight gradients, bias column sums
   // and the modulation-MLP input gradient leave the critical chain for a side stream.  Same kernels, same results.
-  ForkCtx* fc = concurrent_rows(B) ? fork_ctx() : nullptr;
+  ForkCtx* fc = concurrent_rows(B, d) ? fork_ctx() : nullptr;
   const bool conc = fc != nullptr;
   const bool conc_fwd = conc && need_v;
   // z_t -> xs[0] (u pass) and, for improved mean flow without sharing, v (v pass, in place); mean flow seeds the tangent
@@ -804,7 +823,7 @@ int train_step_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, const Mfa
                        0.f, 0.f, nullptr};
   hook.grads = grads;
   hook.world = world;
-  hook.deferred = !(concurrent_rows(B) && fork_ctx() != nullptr);
+  hook.deferred = !(concurrent_rows(B, hook.d) && fork_ctx() != nullptr);
   hook.fc = hook.deferred ? nullptr : fork_ctx();
   if (const char* ev = getenv("MFAC_DP_BUCKET_BLOCKS")) hook.bucket_blocks = atoi(ev) > 0 ? atoi(ev) : 2;
   // bias correction first (host value, or the device counter read and advanced once per step for graph replay)

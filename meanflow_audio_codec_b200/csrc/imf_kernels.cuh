@@ -564,6 +564,158 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(LnBwdArgs a, Dims d, in
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Wide rows (Ip > 2048: the noise-dimension sweep, D = 3584 / 7680): one CTA of 256 threads per row, the row in registers
+// as up to WIDE_MAXV 8-column vectors per thread (v = tid + 256 i), 16/32-byte accesses, block-wide reductions.  Same
+// arithmetic as the warp-per-row kernels above.  Preconditions: D == Dp, L == Lp, Ip <= 8 * 256 * WIDE_MAXV.
+// ---------------------------------------------------------------------------------------
+constexpr int WIDE_MAXV = 4;
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* red /*[32]*/) {
+  v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float2 t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : make_float2(0.f, 0.f);
+  if (w == 0) {
+    t.x = warp_sum(t.x); t.y = warp_sum(t.y);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+template <bool TANGENT>
+__global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
+  MFAC_PDL_SYNC();
+  __shared__ float2 red[32];
+  const int64_t b = a.reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  float c[WIDE_MAXV][8], cd[TANGENT ? WIDE_MAXV : 1][8];
+  float2 s12 = make_float2(0.f, 0.f);
+  float sumd = 0.f;
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i) {
+    const int col = 8 * ((int)threadIdx.x + 256 * i);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { c[i][q] = 0.f; if (TANGENT) cd[i][q] = 0.f; }
+    if (col < d.Ip) {
+      if (col < d.Lp) {
+        if (a.lat) ld8_f32(a.lat + b * d.Lp + col, c[i]);
+      } else {
+        ld8_f32(a.x + b * d.Dp + (col - d.Lp), c[i]);
+        if (TANGENT) ld8_f32(a.xd + b * d.Dp + (col - d.Lp), cd[i]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s12.x += c[i][q];
+      s12.y += c[i][q] * c[i][q];
+      if (TANGENT) sumd += cd[i][q];
+    }
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float2 tot = block_sum2(s12, red);
+  const float mu = tot.x * inv_i;
+  const float rstd = rsqrtf(fmaxf(0.f, tot.y * inv_i - mu * mu) + LN_EPS);
+  float mean_cd = 0.f, mean_ncd = 0.f;
+  if (TANGENT) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < WIDE_MAXV; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += (c[i][q] - mu) * rstd * cd[i][q];   // vectors beyond the row hold zeros
+    const float2 t2 = block_sum2(make_float2(sumd, acc), red);
+    mean_cd = t2.x * inv_i;
+    mean_ncd = t2.y * inv_i;
+  }
+  if (threadIdx.x == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
+  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i) {
+    const int col = 8 * ((int)threadIdx.x + 256 * i);
+    if (col >= d.Ip) continue;
+    float s1[8], sh[8], h[8], n[8];
+    ld8_bf16(mrow + col, s1);
+    ld8_bf16(mrow + d.Ip + col, sh);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      n[q] = (c[i][q] - mu) * rstd;
+      h[q] = (1.0f + s1[q]) * n[q] + sh[q];
+    }
+    if (!TANGENT || a.hin) st8_bf16(a.hin + b * d.Ip + col, h);
+    if (TANGENT) {
+      float s1d[8], shd[8];
+      ld8_bf16(a.md + b * d.Mp + col, s1d);
+      ld8_bf16(a.md + b * d.Mp + d.Ip + col, shd);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float nd = (cd[i][q] - mean_cd - n[q] * mean_ncd) * rstd;
+        h[q] = s1d[q] * n[q] + (1.0f + s1[q]) * nd + shd[q];
+      }
+      st8_bf16(a.hind + b * d.Ip + col, h);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_bwd_wide_kernel(LnBwdArgs a, Dims d) {
+  MFAC_PDL_SYNC();
+  __shared__ float2 red[32];
+  const int64_t b = a.reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  float n[WIDE_MAXV][8], acc[WIDE_MAXV][8], gn[WIDE_MAXV][8];
+  uint4 r_gh[WIDE_MAXV], r_s1[WIDE_MAXV];
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i) {
+    const int col = 8 * ((int)threadIdx.x + 256 * i);
+    r_gh[i] = make_uint4(0u, 0u, 0u, 0u);
+    r_s1[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { n[i][q] = 0.f; acc[i][q] = 0.f; }
+    if (col < d.Ip) {
+      if (col < d.Lp) {
+        ld8_f32(a.lat + b * d.Lp + col, n[i]);
+        ld8_f32(a.g_lat + b * d.Lp + col, acc[i]);
+      } else {
+        ld8_f32(a.x + b * d.Dp + (col - d.Lp), n[i]);
+        ld8_f32(a.g_x + b * d.Dp + (col - d.Lp), acc[i]);
+      }
+      r_gh[i] = ld8_raw(a.g_m + b * d.Mp + d.Ip + col);
+      r_s1[i] = ld8_raw(a.m + b * d.Mp + col);
+    }
+  }
+  const float mu = a.mu[b], rstd = a.rstd[b];
+  float2 s12 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i) {
+    const int col = 8 * ((int)threadIdx.x + 256 * i);
+    float gh[8], s1[8], gs1[8];
+    cvt8_bf16(r_gh[i], gh);
+    cvt8_bf16(r_s1[i], s1);
+    const bool live = col < d.Ip;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      n[i][q] = live ? (n[i][q] - mu) * rstd : 0.f;
+      gn[i][q] = gh[q] * (1.0f + s1[q]);
+      gs1[q] = gh[q] * n[i][q];
+      s12.x += gn[i][q];
+      s12.y += gn[i][q] * n[i][q];
+    }
+    if (live) st8_bf16(a.g_m + b * d.Mp + col, gs1);
+  }
+  const float inv_i = 1.0f / (float)d.I;
+  const float2 tot = block_sum2(s12, red);
+  const float m1 = tot.x * inv_i, m2 = tot.y * inv_i;
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i) {
+    const int col = 8 * ((int)threadIdx.x + 256 * i);
+    if (col >= d.Ip) continue;
+    float* dst = col < d.Lp ? a.g_lat + b * d.Lp + col : a.g_x + b * d.Dp + (col - d.Lp);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[i][q] += (gn[i][q] - m1 - n[i][q] * m2) * rstd;
+    st8_f32(dst, acc[i]);
+  }
+}
+
 // Backward of the block output, fused with the two bias-gradient column sums that read its results:
 //   g_o = g_x (1+s2)/nb -> bf16 (GEMM operand), db2 += colsum(g_o);  g_s2 = g_x o / nb -> g_m[:, 2Ip:], dbc2[s2 part] += colsum.
 // grid (Dp/256, ceil(B/256)); thread = 8 columns x every 8th row of a 256-row slab (same shape as the column-sum kernel).
