@@ -303,8 +303,12 @@ def run_mfac(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(dp.local_rank)
     dev = torch.device("cuda", dp.local_rank)
-    if dp.enabled and os.environ.get("MFAC_DP_TORCH", "0") != "1":
-        dp.init_library_comm()    # the fused step then all-reduces through libmfac's own communicator (mfac_comm_*)
+    if dp.enabled and os.environ.get("MFAC_DP_LIBCOMM", "0") == "1":
+        # Optional: small batches then exchange gradient buckets through libmfac's own communicator (mfac_comm_*) from inside
+        # the fused step.  Not the default: measured on 8 x B200 it is no faster than one torch.distributed all-reduce after the
+        # backward (128 rows / GPU: 1.64 vs 1.54 ms / step; 4096 rows: 3.27 vs 3.23 ms), and a second live communicator alone cost
+        # the run-ahead loop 2 ms / step at 37 888 rows (16.98 vs 15.06 ms; its proxy threads compete with 8 launch threads).
+        dp.init_library_comm()
     T = args.noise_dimension
     nf, D = token_dim(T)
     pk = peaks()

@@ -298,6 +298,8 @@ MFAC_API int mfac_comm_destroy(void);
  * before the call returns.  Default 4096 (env MFAC_CONC_MAX_ROWS); 0 = always the single-stream schedule.  The value also
  * decides the layout mfac_workspace_bytes(MFAC_WS_LOSS_GRAD) sizes: change it before sizing the workspace, not between. */
 MFAC_API int mfac_set_concurrency_max_rows(int32_t rows);
+/* 1 when a batch of B rows of this geometry runs the concurrent schedules (B <= rows and B * D <= rows * 1024), else 0. */
+MFAC_API int mfac_uses_concurrent_schedule(const MfacMlpDims* dims, int64_t B);
 
 /* ------------------------------------------------------------------ test hooks
  * C[M,N] fp32 = A * B with bf16 operands through the production tcgen05 GEMM.

@@ -119,6 +119,7 @@ PROTOTYPES = {
     "mfac_comm_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),
     "mfac_comm_destroy": (C.c_int, []),
     "mfac_set_concurrency_max_rows": (C.c_int, [_I32]),
+    "mfac_uses_concurrent_schedule": (C.c_int, [C.POINTER(MlpDims), _I64]),
     "mfac_debug_gemm_bf16": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
     "mfac_debug_set_simt_gemm": (C.c_int, [_I32]),
     "mfac_debug_set_pair_gemm": (C.c_int, [_I32]),

@@ -745,6 +745,12 @@ int mfac_imf_loss_grad(const MfacMlpDims* dims, const MfacImfConfig* cfg, const 
   return loss_grad_impl(dims, cfg, shadow, x, e, t, r, loss, grads, aux, B, ws, ws_bytes, stream, nullptr);
 }
 
+int mfac_uses_concurrent_schedule(const MfacMlpDims* dims, int64_t B) {
+  Dims d;
+  if (make_dims(dims, &d) != MFAC_SUCCESS || B <= 0) return 0;
+  return concurrent_rows(B, d) ? 1 : 0;
+}
+
 int mfac_imf_loss_grad_audio(const MfacMlpDims* dims, const MfacImfConfig* cfg, const float* params, const void* shadow,
                              const float* audio, int64_t T, int32_t window_size, int32_t hop_size, const float* e, const float* t,
                              const float* r, float* loss, float* grads, const MfacImfAux* aux, int64_t B, void* ws,

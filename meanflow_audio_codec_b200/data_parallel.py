@@ -99,8 +99,19 @@ def train_step_dp(dp: DataParallel, state, key, x_local, loss_strategy, **kw):
     grad_scale = 1/world.  The RNG rows are offset by rank so shards draw independent (e, t, r); the
     "first half gets r = t" rule (utils.py:41-44) is applied per local shard."""
     kw.setdefault("row_offset", dp.rank * x_local.shape[0])
-    if (not dp.enabled or getattr(dp, "fused", False)) and hasattr(loss_strategy, "train_step_fused") and hasattr(state, "tx"):
-        # ONE library call: loss/grad schedule, per-slice NCCL all-reduce over libmfac's own communicator (world > 1) and AdamW
+    fused_ok = hasattr(loss_strategy, "train_step_fused") and hasattr(state, "tx")
+    if fused_ok and dp.enabled and getattr(dp, "fused", False):
+        # Small batches (the library's concurrent schedule): gradient buckets are exchanged over libmfac's own communicator on a
+        # side stream under the rest of the backward (2 x B200, 128 rows / GPU: 1.40 ms / step against 1.80 ms).  Large
+        # batches keep ONE all-reduce after the backward, issued from here: measured on 8 x B200 at 37 888 rows / GPU the same
+        # collective issued from inside the library call cost 16.6 ms / step against 15.1 ms (both communicators move 113 MB
+        # in 345 us when timed alone, tools/comm_probe.py; the host thread cannot run ahead of a collective enqueued mid-call).
+        import ctypes as C
+
+        from . import _lib
+        fused_ok = bool(_lib.lib().mfac_uses_concurrent_schedule(C.byref(state.model.dims), int(x_local.shape[0])))
+    if fused_ok and (not dp.enabled or getattr(dp, "fused", False)):
+        # ONE library call: loss/grad schedule, bucketed NCCL all-reduce over libmfac's own communicator (world > 1) and AdamW
         state, loss, _ = loss_strategy.train_step_fused(state, key, x_local, world=dp.world if dp.enabled else 1, **kw)
         return state, loss, key
     if not dp.enabled:
