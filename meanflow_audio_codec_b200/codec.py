@@ -55,20 +55,24 @@ class MeanFlowCodec:
                 "out_len": (nf - 1) * self.hop + 2 * self.N}
 
     # ------------------------------------------------------------------ stages (device tensors)
-    def tokens(self, audio: torch.Tensor) -> torch.Tensor:
-        """[B, T] -> model rows [B * rows_per_clip, D] (a view of the MDCT output, no copy)."""
+    def tokens(self, audio: torch.Tensor, valid_length: int | None = None) -> torch.Tensor:
+        """[B, T] -> model rows [B * rows_per_clip, D] (a view of the MDCT output, no copy).  ``valid_length``: the clips are
+        ``valid_length`` samples long and ``audio`` is already zero-padded to ``geometry(valid_length)["t_pad"]`` columns (the
+        host-streaming path stages straight into such a buffer, which saves the padding copy)."""
         _lib.require_cuda(audio, "audio")
         if audio.ndim != 2:
             raise ValueError(f"audio must be [B, T], got {tuple(audio.shape)}")
-        g = self.geometry(int(audio.shape[1]))
+        g = self.geometry(int(audio.shape[1]) if valid_length is None else int(valid_length))
+        if valid_length is not None and audio.shape[1] != g["t_pad"]:
+            raise ValueError(f"pre-padded audio must have {g['t_pad']} columns, got {audio.shape[1]}")
         if g["t_pad"] != audio.shape[1]:
             audio = torch.nn.functional.pad(audio, (0, g["t_pad"] - audio.shape[1]))
         X = mdct(audio, self.N, self.hop, **self._fft_kw)            # [B, nf_pad, N]
         return X.view(-1, self.model.noise_dimension)
 
-    def encode(self, audio: torch.Tensor) -> torch.Tensor:
+    def encode(self, audio: torch.Tensor, valid_length: int | None = None) -> torch.Tensor:
         """[B, T] -> latents [B * rows_per_clip, L]."""
-        return self.model.apply({"params": self.params}, self.tokens(audio), method="encode")
+        return self.model.apply({"params": self.params}, self.tokens(audio, valid_length), method="encode")
 
     def decode(self, latents: torch.Tensor, clips: int, T: int, sampler: str = "mf", nfe: int = 1, key: int = 0,
                guidance_scale: float = 1.0, noise=None) -> torch.Tensor:
@@ -86,9 +90,10 @@ class MeanFlowCodec:
         return y[:, :g["out_len"]]                                    # crop is a view
 
     def reconstruct(self, audio: torch.Tensor, sampler: str = "mf", nfe: int = 1, key: int = 0,
-                    guidance_scale: float = 1.0) -> torch.Tensor:
-        lat = self.encode(audio)
-        return self.decode(lat, audio.shape[0], int(audio.shape[1]), sampler, nfe, key, guidance_scale)
+                    guidance_scale: float = 1.0, valid_length: int | None = None) -> torch.Tensor:
+        lat = self.encode(audio, valid_length)
+        T = int(audio.shape[1]) if valid_length is None else int(valid_length)
+        return self.decode(lat, audio.shape[0], T, sampler, nfe, key, guidance_scale)
 
     # ------------------------------------------------------------------ host buffers, streamed
     def reconstruct_host(self, audio_host: torch.Tensor, out_host: torch.Tensor | None = None, sampler: str = "mf",
@@ -108,7 +113,8 @@ class MeanFlowCodec:
         sb = max(1, min(int(sub_batch), B))
         compute = torch.cuda.current_stream(dev)
         up, down = self._streams(dev)
-        x_dev = [torch.empty((sb, T), dtype=torch.float32, device=dev) for _ in range(2)]
+        # device slots are as wide as the padded clip and zero beyond T: uploads land in [:, :T], no padding copy afterwards
+        x_dev = [torch.zeros((sb, g["t_pad"]), dtype=torch.float32, device=dev) for _ in range(2)]
         y_dev = [torch.empty((sb, g["out_len"]), dtype=torch.float32, device=dev) for _ in range(2)]
         uploaded = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]     # x slot free again
@@ -123,7 +129,7 @@ class MeanFlowCodec:
             s = j & 1
             with torch.cuda.stream(up):
                 up.wait_event(consumed[s])
-                x_dev[s][:b - a].copy_(audio_host[a:b], non_blocking=True)
+                x_dev[s][:b - a, :T].copy_(audio_host[a:b], non_blocking=True)
                 uploaded[s].record(up)
 
         upload(0)
@@ -133,7 +139,7 @@ class MeanFlowCodec:
             if j + 1 < len(chunks):
                 upload(j + 1)
             compute.wait_event(drained[s])
-            y = self.reconstruct(x_dev[s][:b - a], sampler=sampler, nfe=nfe, key=key + j)
+            y = self.reconstruct(x_dev[s][:b - a], sampler=sampler, nfe=nfe, key=key + j, valid_length=T)
             y_dev[s][:b - a].copy_(y)
             consumed[s].record(compute)
             produced[s].record(compute)
