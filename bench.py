@@ -469,7 +469,8 @@ def run_mfac(args):
         model = state = strat = tok = x_raw = None
         torch.cuda.empty_cache()
         noise_sweep = {}
-        for Tn, bn in ((2048, 8192), (4096, 4096)):
+        # batches = whole waves of 256-row tile pairs on 74 SM pairs (18 944 = 74 pairs, 9472 = 37), like the headline's 37 888
+        for Tn, bn in ((2048, 18944), (4096, 9472)):
             try:
                 r = timed(bn, 3, 3, Tm=Tn, profile=True)
                 nfn, Dn = token_dim(Tn)
