@@ -509,6 +509,10 @@ def run_mfac(args):
             "tensor_frac_whole_step": ((roofline["flops_per_step_measured"] if roofline else flops_per_sample(D) * B)
                                        / (main_ms * 1e-3) / 1e12 / pk["bf16_sustained"]),
             "tensor_frac_whole_step_reference_flops": flops_per_sample(D) * B / (main_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+            # SURVEY.md section 8d config 2 (the audio config's hyper-parameters at tractable noise dimensions): where the tensor
+            # roof binds, whole step on executed FLOPs
+            "tensor_frac_whole_step_by_noise_dimension": ({k: v.get("tensor_frac_whole_step") for k, v in sweep["noise_dimension"].items()}
+                                                          if sweep and "noise_dimension" in sweep else None),
             "kernel_families": families, "sweep": sweep, "codec": codec, "matching_batch": matching,
             "scaling_small": scaling_small, "csrc_hash": csrc_hash(),
             "wall_ms_per_step": main_wall / args.steps, "loss": main_loss,
@@ -721,7 +725,8 @@ def main():
     ap.add_argument("--impl", default="mfac", choices=["mfac", "reference"])
     ap.add_argument("--batch", type=int, default=37888, help="per-GPU batch (2 x 148 SMs x 128-row tiles)")
     ap.add_argument("--noise-dimension", type=int, default=784, help="raw samples per example (T)")
-    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 4096, 18944])
+    ap.add_argument("--sweep", type=int, nargs="*", default=[128, 1024, 4096, 16384, 18944],
+                    help="other per-GPU batches (SURVEY.md section 8d: 128 = the config's own, 1024, 4096, 16384; 18944 = one wave of tile pairs)")
     ap.add_argument("--quick", action="store_true", help="skip sweep / codec / cpu baseline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mfac":

@@ -592,6 +592,10 @@ __global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
   __shared__ float2 red[32];
   const int64_t b = a.reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
   float c[WIDE_MAXV][8], cd[TANGENT ? WIDE_MAXV : 1][8];
+  // every load of the row (data and modulation, primal and tangent) is requested before the first reduction: one memory round
+  // trip per row instead of one per phase (the CTA is the only thing hiding latency here)
+  uint4 r_s1[WIDE_MAXV], r_sh[WIDE_MAXV], r_s1d[TANGENT ? WIDE_MAXV : 1], r_shd[TANGENT ? WIDE_MAXV : 1];
+  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
   float2 s12 = make_float2(0.f, 0.f);
   float sumd = 0.f;
 #pragma unroll
@@ -599,6 +603,9 @@ __global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
     const int col = 8 * ((int)threadIdx.x + 256 * i);
 #pragma unroll
     for (int q = 0; q < 8; ++q) { c[i][q] = 0.f; if (TANGENT) cd[i][q] = 0.f; }
+    r_s1[i] = make_uint4(0u, 0u, 0u, 0u);
+    r_sh[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (TANGENT) { r_s1d[i] = make_uint4(0u, 0u, 0u, 0u); r_shd[i] = make_uint4(0u, 0u, 0u, 0u); }
     if (col < d.Ip) {
       if (col < d.Lp) {
         if (a.lat) ld8_f32(a.lat + b * d.Lp + col, c[i]);
@@ -606,14 +613,22 @@ __global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
         ld8_f32(a.x + b * d.Dp + (col - d.Lp), c[i]);
         if (TANGENT) ld8_f32(a.xd + b * d.Dp + (col - d.Lp), cd[i]);
       }
+      r_s1[i] = ld8_raw(mrow + col);
+      r_sh[i] = ld8_raw(mrow + d.Ip + col);
+      if (TANGENT) {
+        r_s1d[i] = ld8_raw(a.md + b * d.Mp + col);
+        r_shd[i] = ld8_raw(a.md + b * d.Mp + d.Ip + col);
+      }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < WIDE_MAXV; ++i)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       s12.x += c[i][q];
       s12.y += c[i][q] * c[i][q];
       if (TANGENT) sumd += cd[i][q];
     }
-  }
   const float inv_i = 1.0f / (float)d.I;
   const float2 tot = block_sum2(s12, red);
   const float mu = tot.x * inv_i;
@@ -622,22 +637,23 @@ __global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
   if (TANGENT) {
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < WIDE_MAXV; ++i)
+    for (int i = 0; i < WIDE_MAXV; ++i) {
+      const bool live = 8 * ((int)threadIdx.x + 256 * i) < d.Ip;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc += (c[i][q] - mu) * rstd * cd[i][q];   // vectors beyond the row hold zeros
+      for (int q = 0; q < 8; ++q) acc += live ? (c[i][q] - mu) * rstd * cd[i][q] : 0.f;
+    }
     const float2 t2 = block_sum2(make_float2(sumd, acc), red);
     mean_cd = t2.x * inv_i;
     mean_ncd = t2.y * inv_i;
   }
   if (threadIdx.x == 0 && a.mu) { a.mu[b] = mu; a.rstd[b] = rstd; }
-  const __nv_bfloat16* mrow = a.m + b * a.m_stride;
 #pragma unroll
   for (int i = 0; i < WIDE_MAXV; ++i) {
     const int col = 8 * ((int)threadIdx.x + 256 * i);
     if (col >= d.Ip) continue;
     float s1[8], sh[8], h[8], n[8];
-    ld8_bf16(mrow + col, s1);
-    ld8_bf16(mrow + d.Ip + col, sh);
+    cvt8_bf16(r_s1[i], s1);
+    cvt8_bf16(r_sh[i], sh);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       n[q] = (c[i][q] - mu) * rstd;
@@ -646,8 +662,8 @@ __global__ void __launch_bounds__(256) lnmod_wide_kernel(LnModArgs a, Dims d) {
     if (!TANGENT || a.hin) st8_bf16(a.hin + b * d.Ip + col, h);
     if (TANGENT) {
       float s1d[8], shd[8];
-      ld8_bf16(a.md + b * d.Mp + col, s1d);
-      ld8_bf16(a.md + b * d.Mp + d.Ip + col, shd);
+      cvt8_bf16(r_s1d[i], s1d);
+      cvt8_bf16(r_shd[i], shd);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float nd = (cd[i][q] - mean_cd - n[q] * mean_ncd) * rstd;
