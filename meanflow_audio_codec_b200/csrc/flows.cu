@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "epilogues.cuh"
 #include "imf_layout.cuh"
+#include "mixer_fused.cuh"
 
 namespace mfac {
 namespace {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) mixer_adaln_kernel(float* __restrict__ u,
 
 struct MixerPlan {
   float *x, *latc, *ss1, *ss2, *u, *t2;
-  __nv_bfloat16 *xb, *cond, *latb, *a1, *h1, *a2, *h2, *u3;
+  __nv_bfloat16 *xb, *cond, *latb, *a1, *h1, *a2, *h2, *u3, *w2t;
   void plan(Arena& ar, const MfacMixerDims& d, int64_t B) {
     const int64_t TC = (int64_t)d.tokens * d.channels;
     x = ar.take<float>(B * d.D);
@@ -120,6 +121,7 @@ struct MixerPlan {
     a2 = ar.take<__nv_bfloat16>(B * TC);
     h2 = ar.take<__nv_bfloat16>(B * (int64_t)d.tokens * d.channel_mix);
     u3 = ar.take<__nv_bfloat16>(B * TC);
+    w2t = ar.take<__nv_bfloat16>((int64_t)d.channel_mix * d.channels);   // transposed second channel-mix kernel (fused path)
   }
 };
 
@@ -159,9 +161,16 @@ int mixer_forward_impl(const MfacMixerDims& d, const MfacMixerWeights& w, const 
     MFAC_OK(dense(p.cond, d.C, bw.adaln2, M, 2 * CH, d.C, EpiLinearF32{bw.adaln2.b, p.ss2, 2 * CH}, s));
     mixer_adaln_kernel<CH, false><<<nblk(B * d.tokens, 256), 256, 0, s>>>(p.u, p.t2, p.ss2, p.a2, d.tokens, B);
     count_launch();
-    MFAC_OK(dense(p.a2, CH, bw.ch1, M * d.tokens, d.channel_mix, CH, EpiBiasGelu{bw.ch1.b, p.h2, nullptr, d.channel_mix}, s));
-    MFAC_OK(dense(p.h2, d.channel_mix, bw.ch2, M * d.tokens, CH, d.channel_mix,
-                  EpiAffineResidual{bw.ch2.b, p.u, nullptr, p.u3, CH, 1.0f}, s));
+    // both channel-mix layers in ONE kernel (the [B * tokens, channel_mix] hidden tensor stays on the SM); other geometries
+    // run the two GEMMs through HBM
+    const int fused = channel_mix_fused(p.a2, bw.ch1, bw.ch2, p.w2t, p.u, p.u3, (int64_t)M * d.tokens, CH, d.channel_mix, s);
+    if (fused == MFAC_ERR_UNSUPPORTED) {
+      MFAC_OK(dense(p.a2, CH, bw.ch1, M * d.tokens, d.channel_mix, CH, EpiBiasGelu{bw.ch1.b, p.h2, nullptr, d.channel_mix}, s));
+      MFAC_OK(dense(p.h2, d.channel_mix, bw.ch2, M * d.tokens, CH, d.channel_mix,
+                    EpiAffineResidual{bw.ch2.b, p.u, nullptr, p.u3, CH, 1.0f}, s));
+    } else {
+      MFAC_OK(fused);
+    }
     // output_proj, x / num_blocks + residual                                     (:157-163)
     MFAC_OK(dense(p.u3, TC, bw.output_proj, M, d.D, TC, EpiAffineResidual{bw.output_proj.b, p.x, p.x, p.xb, d.D, inv_nb}, s));
   }
