@@ -25,14 +25,17 @@ import torch
 
 from . import _lib
 from .mdct import imdct, mdct, num_frames
+from .flows import _FlowBase
 from .mlp_flow import ConditionalFlow
 from .sampling import sample, sample_mean_flow
 
 
 class MeanFlowCodec:
-    def __init__(self, model: ConditionalFlow, params, window_size: int = 512, hop_size: int | None = None):
-        if not isinstance(model, ConditionalFlow):
-            raise TypeError("model must be a ConditionalFlow")
+    def __init__(self, model, params, window_size: int = 512, hop_size: int | None = None):
+        """``model``: a ``ConditionalFlow``, or a ``ConditionalMLPMixerFlow`` / ``ConditionalConvFlow`` built with
+        ``num_latent_tokens=1`` and initialised ``with_encoder=True`` (flows.py)."""
+        if not isinstance(model, (ConditionalFlow, _FlowBase)):
+            raise TypeError("model must be a ConditionalFlow, ConditionalMLPMixerFlow or ConditionalConvFlow")
         self.model, self.params = model, params
         self.N = int(window_size)
         self.hop = int(hop_size) if hop_size is not None else self.N // 2
@@ -71,12 +74,12 @@ class MeanFlowCodec:
         return X.view(-1, self.model.noise_dimension)
 
     def encode(self, audio: torch.Tensor, valid_length: int | None = None) -> torch.Tensor:
-        """[B, T] -> latents [B * rows_per_clip, L]."""
+        """[B, T] -> latents [B * rows_per_clip, L]  ([.., 1, L] for the mixer / ConvNeXt flows)."""
         return self.model.apply({"params": self.params}, self.tokens(audio, valid_length), method="encode")
 
     def decode(self, latents: torch.Tensor, clips: int, T: int, sampler: str = "mf", nfe: int = 1, key: int = 0,
                guidance_scale: float = 1.0, noise=None) -> torch.Tensor:
-        """latents [clips * rows_per_clip, L] -> audio [clips, (nf - 1) * hop + 2N]."""
+        """latents [clips * rows_per_clip, L] (or [.., 1, L]) -> audio [clips, (nf - 1) * hop + 2N]."""
         g = self.geometry(T)
         D = self.model.noise_dimension
         if sampler == "mf":

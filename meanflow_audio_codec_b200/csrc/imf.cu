@@ -349,6 +349,7 @@ extern "C" {
 size_t mfac_workspace_bytes(int32_t kind, const MfacMlpDims* dims, int64_t B) {
   Dims d;
   if (make_dims(dims, &d) != MFAC_SUCCESS || B <= 0 || d.nb > 64) return 0;
+  if (d.nb < 1 && kind != MFAC_WS_FORWARD) return 0;
   Arena ar(nullptr, 0);
   if (kind == MFAC_WS_FORWARD) { ForwardPlan p; p.plan(ar, d, B); }
   else if (kind == MFAC_WS_LOSS_GRAD) { LossGradPlan p; p.plan(ar, d, B); }
@@ -387,7 +388,7 @@ int mfac_mlp_forward(const MfacMlpDims* dims, const float* params, const void* s
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!shadow || !x || !time || !out) return MFAC_ERR_NULL;
-  if (B <= 0 || B > 0x7fffffff || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if (B <= 0 || B > 0x7fffffff || d.nb > 64 || d.nb < 1) return MFAC_ERR_BAD_SHAPE;
   if (!ws) return MFAC_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
@@ -437,13 +438,14 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!cfg || !shadow || (!x && !audio) || !loss || !grads) return MFAC_ERR_NULL;
+  if (d.nb < 1) return MFAC_ERR_BAD_SHAPE;
   if (audio) {
     if (!audio->audio) return MFAC_ERR_NULL;
     if (audio->T <= 0 || audio->N <= 0 || audio->hop <= 0) return MFAC_ERR_BAD_SHAPE;
     const int64_t nf = audio->T < audio->N ? 1 : (audio->T - audio->N) / audio->hop + 1;
     if (nf * audio->N != d.D) return MFAC_ERR_BAD_SHAPE;   // the tokens of a clip are one model row
   }
-  if (B <= 0 || B > 0x7fffffff || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if (B <= 0 || B > 0x7fffffff || d.nb > 64 || d.nb < 1) return MFAC_ERR_BAD_SHAPE;
   if ((t == nullptr) != (r == nullptr)) return MFAC_ERR_NULL;
   if (!ws) return MFAC_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -872,7 +874,7 @@ int mfac_sample(const MfacMlpDims* dims, const float* params, const void* shadow
   Dims d;
   MFAC_OK(make_dims(dims, &d));
   if (!shadow || !latents || !out) return MFAC_ERR_NULL;
-  if (B <= 0 || B > 0x7fffffff || n_steps <= 0 || d.nb > 64) return MFAC_ERR_BAD_SHAPE;
+  if (B <= 0 || B > 0x7fffffff || n_steps <= 0 || d.nb > 64 || d.nb < 1) return MFAC_ERR_BAD_SHAPE;
   if (mode != MFAC_SAMPLE_HEUN && mode != MFAC_SAMPLE_MF) return MFAC_ERR_UNSUPPORTED;
   if (!ws) return MFAC_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;

@@ -62,7 +62,9 @@ struct Dims {
 
 inline int make_dims(const MfacMlpDims* d, Dims* out) {
   if (!d) return MFAC_ERR_NULL;
-  if (d->D <= 0 || d->L <= 0 || d->C <= 0 || d->nb <= 0 || (d->C & 1)) return MFAC_ERR_BAD_SHAPE;
+  // nb == 0 is the encoder on its own (layout = the four encoder leaves): accepted by mfac_mlp_encode, the casts and AdamW;
+  // every entry point that evaluates the velocity network asks for nb >= 1 itself.
+  if (d->D <= 0 || d->L <= 0 || d->C <= 0 || d->nb < 0 || (d->C & 1)) return MFAC_ERR_BAD_SHAPE;
   Dims x{};
   x.D = d->D; x.L = d->L; x.C = d->C; x.nb = d->nb;
   x.I = x.L + x.D;

@@ -14,6 +14,12 @@ name, ``@nn.compact`` ones auto-numbered in call order):
            Conv_2 (1x1 contract), layer_scale_gamma}}, latent_proj
 ref: models/mlp_mixer.py:14-235, models/conv_flow.py:14-271, models/factories.py:106-148.
 The reference never trains these two models (they have no ``encode``), so there is no loss path.
+
+Encoder wiring ("smallest faithful choice"): ``init(key, with_encoder=True)`` adds the MLP flow's
+``encoder`` subtree (mlp_flow.py:153-162: Dense -> GELU -> Dense, D -> (D + L) / 2 -> L) and
+``apply(variables, x, method="encode")`` returns ``latents[B, 1, L]``, which the model's own ``latent_proj`` consumes when it was
+built with ``num_latent_tokens=1``.  That is what lets ``MeanFlowCodec`` run MDCT -> encode -> sample -> IMDCT with any of the
+three architectures.
 """
 from __future__ import annotations
 
@@ -95,8 +101,32 @@ class _FlowBase:
                 raise ValueError(f"latents must flatten to [B, {self.latent_flat}], got {tuple(latents.shape)}")
         return x, time, latents, B
 
-    def __call__(self, variables, x, time, latents=None):
-        return self.apply(variables, x, time, latents)
+    def __call__(self, variables, x, time=None, latents=None, method=None):
+        return self.apply(variables, x, time, latents, method=method)
+
+    # ---------------------------------------------------------------- encoder wiring
+    def _encoder_model(self):
+        from .mlp_flow import ConditionalFlow
+        if getattr(self, "_enc_model", None) is None:
+            # num_blocks = 0: the flat layout is the four encoder leaves and nothing else (csrc/imf_layout.cuh make_dims)
+            self._enc_model, self._enc_fp = ConditionalFlow(self.noise_dimension, 2, 0, self.latent_dimension), None
+        return self._enc_model
+
+    def _init_encoder(self, gen, device) -> dict:
+        return self._encoder_model().init(gen, device=device)["params"]["encoder"]
+
+    def encode(self, params, x: torch.Tensor) -> torch.Tensor:
+        """x[B, D] -> latents[B, 1, L] through the MLP encoder stored under ``params["encoder"]``."""
+        if self.num_latent_tokens != 1:
+            raise ValueError("encode() feeds latents[B, 1, L] to latent_proj: build the model with num_latent_tokens=1")
+        if "encoder" not in params:
+            raise KeyError("params has no 'encoder' subtree (use init(key, with_encoder=True))")
+        enc = self._encoder_model()
+        leaves = [params["encoder"]["encoder_mlp"][d][k] for d in ("dense1", "dense2") for k in ("bias", "kernel")]
+        tag = tuple((id(t), t._version) for t in leaves)
+        if self._enc_fp is None or self._enc_fp[0] != tag:
+            self._enc_fp = (tag, enc.flat_params({"encoder": params["encoder"]}), leaves)   # leaves pinned: ids stay unique
+        return enc.encode(self._enc_fp[1], x)[:, None, :]
 
 
 class ConditionalMLPMixerFlow(_FlowBase):
@@ -116,7 +146,7 @@ class ConditionalMLPMixerFlow(_FlowBase):
         return _lib.MixerDims(self.noise_dimension, self.condition_dimension, self.num_blocks, self.num_tokens,
                               self.num_channels, self.token_mix_dim, self.channel_mix_dim, self.latent_flat)
 
-    def init(self, key=0, *args, device="cuda", **kwargs) -> dict:
+    def init(self, key=0, *args, device="cuda", with_encoder: bool = False, **kwargs) -> dict:
         gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(int(key))
         D, Cd, T, ch = self.noise_dimension, self.condition_dimension, self.num_tokens, self.num_channels
         p = {}
@@ -131,9 +161,18 @@ class ConditionalMLPMixerFlow(_FlowBase):
                 "output_proj": _dense(T * ch, D, gen),
             }
         p["latent_proj"] = _dense(self.latent_flat, Cd, gen)
-        return {"params": _to_device(p, device)}
+        p = _to_device(p, device)
+        if with_encoder:
+            p["encoder"] = self._init_encoder(gen, device)
+        return {"params": p}
 
-    def apply(self, variables, x, time, latents=None):
+    def apply(self, variables, x, time=None, latents=None, method=None):
+        if method == "encode":
+            return self.encode(variables["params"], x)
+        if method is not None:
+            raise ValueError(f"unknown method {method!r}")
+        if time is None:
+            raise TypeError("apply() missing required argument: 'time'")
         x, time, latents, B = self._check(x, time, latents)
         p = variables["params"]
         c = self._cache
@@ -180,7 +219,7 @@ class ConditionalConvFlow(_FlowBase):
         return _lib.ConvDims(self.noise_dimension, self.condition_dimension, self.num_blocks, self.spatial_size,
                              self.channels, self.bottleneck, self.latent_flat)
 
-    def init(self, key=0, *args, device="cuda", **kwargs) -> dict:
+    def init(self, key=0, *args, device="cuda", with_encoder: bool = False, **kwargs) -> dict:
         gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(int(key))
         D, Cd, S, ch, bn = self.noise_dimension, self.condition_dimension, self.spatial_size, self.channels, self.bottleneck
         p = {}
@@ -198,9 +237,18 @@ class ConditionalConvFlow(_FlowBase):
                 "output_proj1": _dense(S * S * ch, bn, gen), "output_proj2": _dense(bn, D, gen),
             }
         p["latent_proj"] = _dense(self.latent_flat, Cd, gen)
-        return {"params": _to_device(p, device)}
+        p = _to_device(p, device)
+        if with_encoder:
+            p["encoder"] = self._init_encoder(gen, device)
+        return {"params": p}
 
-    def apply(self, variables, x, time, latents=None):
+    def apply(self, variables, x, time=None, latents=None, method=None):
+        if method == "encode":
+            return self.encode(variables["params"], x)
+        if method is not None:
+            raise ValueError(f"unknown method {method!r}")
+        if time is None:
+            raise TypeError("apply() missing required argument: 'time'")
         x, time, latents, B = self._check(x, time, latents)
         p = variables["params"]
         c = self._cache

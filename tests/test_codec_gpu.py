@@ -68,3 +68,45 @@ def test_host_streaming_equals_device_path():
         codec.reconstruct_host(x.cuda())
     with pytest.raises(ValueError):
         codec.decode(codec.encode(x.cuda()), B, T, sampler="euler")
+
+
+@pytest.mark.parametrize("arch", ["mlp_mixer", "convnet"])
+def test_codec_with_the_other_architectures(arch):
+    """SURVEY.md section 8f-1 encoder wiring: MLPEncoder -> latents[B, 1, L] -> the mixer's / ConvNeXt's own latent_proj;
+    MDCT -> encode -> 1-NFE mean-flow jump -> IMDCT against the same pipeline over the NumPy oracle."""
+    import meanflow_audio_codec_b200 as m
+    from oracle import flows_np, imf_np, mdct_np
+    from tests.helpers import as64, tree_to_np
+    D, C, nb, L = 1024, 32, 2, 16
+    if arch == "mlp_mixer":
+        model = m.ConditionalMLPMixerFlow(D, C, nb, latent_dimension=L, token_mix_dim=128, channel_mix_dim=128,
+                                          num_channels=16, num_latent_tokens=1)
+        fwd = lambda p, x, t, lat: flows_np.mixer_forward(p, x, t, lat, num_blocks=nb, num_channels=16, condition_dimension=C)  # noqa: E731
+    else:
+        model = m.ConditionalConvFlow(D, C, nb, latent_dimension=L, num_latent_tokens=1)
+        fwd = lambda p, x, t, lat: flows_np.conv_forward(p, x, t, lat, num_blocks=nb, condition_dimension=C)  # noqa: E731
+    from tests.test_flows_gpu import perturb, tree_np
+    params = model.init(11, with_encoder=True)["params"]
+    perturb(params, torch.Generator().manual_seed(2))
+    codec = m.MeanFlowCodec(model, params, window_size=512, hop_size=256)
+    B, T = 2, 3000
+    rng = np.random.default_rng(1)
+    x = (0.1 * rng.standard_normal((B, T))).astype(np.float32)
+    g = codec.geometry(T)
+    rows = B * g["rows_per_clip"]
+    noise = rng.standard_normal((rows, D)).astype(np.float32)
+    lat = codec.encode(torch.from_numpy(x).cuda())
+    assert tuple(lat.shape) == (rows, 1, L)
+    y = codec.decode(lat, B, T, sampler="mf", nfe=1, noise=torch.from_numpy(noise).cuda()).cpu().numpy()
+    p = as64(tree_to_np(params))
+    X = mdct_np.mdct(np.pad(x.astype(np.float64), ((0, 0), (0, g["t_pad"] - T))), 512, 256).reshape(rows, D)
+    lat_o = imf_np.encode(p, X)
+    np.testing.assert_allclose(lat.cpu().numpy()[:, 0], lat_o, rtol=0, atol=2e-2 * np.abs(lat_o).max())
+    e = noise.astype(np.float64)
+    rec = e - fwd(tree_np(params), e, np.tile([[1.0, 1.0]], (rows, 1)), lat_o[:, None, :])
+    y_o = mdct_np.imdct(rec.reshape(B, g["nf_pad"], 512), 512, 256)[:, :g["out_len"]]
+    err = np.linalg.norm(y - y_o) / np.linalg.norm(y_o)
+    assert err < 1e-2, err
+    # no encoder subtree / wrong token count fail loudly
+    with pytest.raises(KeyError):
+        model.apply({"params": {k: v for k, v in params.items() if k != "encoder"}}, torch.zeros(1, D, device="cuda"), method="encode")

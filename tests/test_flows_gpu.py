@@ -34,11 +34,11 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("D,C,nb,tm,cm,ch,B,with_lat", [
-    (64, 32, 2, 64, 64, 16, 5, True),
+    (64, 32, 2, 64, 64, 16, 5, True),            # fused channel mix with a ragged last token tile (320 tokens = 2.5 tiles)
     (64, 32, 1, 128, 96, 8, 3, False),
     (1024, 128, 2, 2048, 2048, 16, 4, True),     # the reference's default widths at D = 1024
     (1024, 32, 1, 64, 192, 16, 20, False),       # fused channel mix: 160 token tiles (> 148 SMs: two tiles on some CTAs), 3 chunks
-    (256, 32, 1, 64, 128, 16, 3, True),          # fused channel mix: ragged last token tile (768 tokens = 6 tiles)
+    (256, 32, 1, 64, 128, 16, 3, True),          # fused channel mix: 2 chunks, latents
 ])
 def test_mixer_forward(m, D, C, nb, tm, cm, ch, B, with_lat):
     from oracle import flows_np
