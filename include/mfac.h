@@ -78,7 +78,8 @@ typedef struct MfacMlpDims {
   int32_t D;  /* noise_dimension (tokens flattened: nf * N) */
   int32_t L;  /* latent_dimension */
   int32_t C;  /* condition_dimension (even) */
-  int32_t nb; /* num_blocks */
+  int32_t nb; /* num_blocks; 0 = the encoder on its own (layout = the four encoder leaves): accepted by the layout queries,
+               * mfac_mlp_cast_params, mfac_mlp_encode and AdamW, MFAC_ERR_BAD_SHAPE everywhere the velocity network is evaluated */
 } MfacMlpDims;
 
 enum MfacParamId {

@@ -66,6 +66,19 @@ def test_param_layout_matches_flax_tree_order(lib, D, L, Cd, nb):
     assert lib.mfac_mlp_shadow_bytes(C.byref(dims)) >= 2 * (total - (sum(int(np.prod(s)) for n, s in shapes if n.endswith("bias"))))
 
 
+def test_encoder_only_layout(lib):
+    """num_blocks = 0: the MLP encoder on its own (what the mixer / ConvNeXt flows use for ``method="encode"``)."""
+    D, L = 1024, 256
+    dims = _lib.MlpDims(D, L, 2, 0)
+    He = (D + L) // 2
+    assert lib.mfac_mlp_param_count(C.byref(dims)) == He + D * He + L + He * L
+    assert lib.mfac_workspace_bytes(_lib.WS_FORWARD, C.byref(dims), 16) > 0
+    assert lib.mfac_workspace_bytes(_lib.WS_LOSS_GRAD, C.byref(dims), 16) == 0      # no velocity network to train
+    assert lib.mfac_workspace_bytes(_lib.WS_SAMPLE, C.byref(dims), 16) == 0
+    enc = m.ConditionalFlow(D, 2, 0, L)
+    assert list(enc.leaf_slices())[0][0] == "encoder" and enc.param_count() == He + D * He + L + He * L
+
+
 def test_bad_dims_are_rejected(lib):
     bad = _lib.MlpDims(8, 64, 31, 2)  # odd condition dimension
     assert lib.mfac_mlp_param_count(C.byref(bad)) < 0
