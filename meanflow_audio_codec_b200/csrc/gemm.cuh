@@ -365,6 +365,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      // Shared-memory descriptors of stage 0, built once: the single issuing thread is on the critical path of narrow tiles
+      // (a 64-column k-block is 128 clocks of tensor work), so the k loop only adds to the start-address field.
+      // K-major: 16 elements = 32 B inside the 128-B swizzle row; MN-major: 16 k-rows of 128 B = 2048 B (SBO apart).
+      const uint64_t a_desc0 = A_MN ? umma_smem_desc_sw128(smem_u32(sA), 8192, 1024) : umma_smem_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = B_MN ? umma_smem_desc_sw128(smem_u32(sB), 8192, 1024) : umma_smem_desc_sw128(smem_u32(sB), 16, 1024);
+      constexpr int a_kk = (A_MN ? 2048 : 32) >> 4, b_kk = (B_MN ? 2048 : 32) >> 4;
       uint32_t kit = 0, it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int sp = item % shape.splits;
@@ -380,18 +386,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t ph = (kit / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          // stage s, k-step kk: only the 14-bit start-address field (bytes >> 4) of the stage-0 descriptors moves
+          const uint64_t ad = a_desc0 + (uint64_t)(s * (int)(Cfg::A_BYTES >> 4));
+          const uint64_t bd = b_desc0 + (uint64_t)(s * (int)(Cfg::B_BYTES >> 4));
 #pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-            // K-major: advance 16 elements = 32 B inside the 128-B swizzle row.
-            // MN-major: advance 16 k-rows of 128 B = 2048 B (two 8-row swizzle atoms, SBO apart).
-            const uint64_t ad = A_MN ? umma_smem_desc_sw128(a_addr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t bd = B_MN ? umma_smem_desc_sw128(b_addr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+            umma_bf16(tmem_d, ad + (uint64_t)(kk * a_kk), bd + (uint64_t)(kk * b_kk), idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs retire
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete
@@ -610,6 +610,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CTRL));
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, A_MN, B_MN);
+      // Shared-memory descriptors of stage 0, built once: the single issuing thread is on the critical path of narrow tiles
+      // (a 64-column k-block is 128 clocks of tensor work), so the k loop only adds to the start-address field.
+      // K-major: 16 elements = 32 B inside the 128-B swizzle row; MN-major: 16 k-rows of 128 B = 2048 B (SBO apart).
+      const uint64_t a_desc0 = A_MN ? umma_smem_desc_sw128(smem_u32(sA), 8192, 1024) : umma_smem_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = B_MN ? umma_smem_desc_sw128(smem_u32(sB), 8192, 1024) : umma_smem_desc_sw128(smem_u32(sB), 16, 1024);
+      constexpr int a_kk = (A_MN ? 2048 : 32) >> 4, b_kk = (B_MN ? 2048 : 32) >> 4;
       uint32_t kit = 0, it = 0;
       SegIter segs(shape, m_tiles * n_tiles, k_blocks_total, pair, npairs);
       Seg sg;
@@ -625,16 +631,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t ph = (kit / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          // stage s, k-step kk: only the 14-bit start-address field (bytes >> 4) of the stage-0 descriptors moves
+          const uint64_t ad = a_desc0 + (uint64_t)(s * (int)(Cfg::A_BYTES >> 4));
+          const uint64_t bd = b_desc0 + (uint64_t)(s * (int)(Cfg::B_BYTES >> 4));
 #pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-            const uint64_t ad = A_MN ? umma_smem_desc_sw128(a_addr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t bd = B_MN ? umma_smem_desc_sw128(b_addr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+            umma_bf16_pair(tmem_d, ad + (uint64_t)(kk * a_kk), bd + (uint64_t)(kk * b_kk), idesc, (kb > kb0 || kk != 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[s]);   // both CTAs' stage s reusable once these MMAs retire
         }
         umma_commit_pair(&tfull_bar[as]);    // accumulator complete in both TMEMs
