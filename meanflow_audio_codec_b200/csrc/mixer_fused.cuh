@@ -174,14 +174,17 @@ channel_mix_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     // K-major 128B-swizzled A tile: row r at r * 128 B, 16-byte piece p at p ^ (r & 7)
     uint4* rowp = reinterpret_cast<uint4*>(sH + team * 16384 + row_in_tile * 128);
     const uint32_t acc1_addr = tmem_base + lane_sel + team * CM_CHUNK;
-    auto gelu_pack = [&](const float (&acc)[32], const float* bias, uint32_t (&o)[16]) {
+    // 16 accumulator columns -> bias, GELU, bf16 -> pieces 2 j, 2 j + 1 of this lane's row of the hidden tile
+    auto gelu_store = [&](const float (&acc)[16], const float* bias, int j) {
+      uint32_t o[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 pre = add4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), ldg_f4(bias + 4 * q));
-        const float4 g = gelu_fast4(pre);
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = gelu_fast4(add4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), ldg_f4(bias + 4 * q)));
         o[2 * q] = pack_bf16(g.x, g.y);
         o[2 * q + 1] = pack_bf16(g.z, g.w);
       }
+      rowp[(2 * j) ^ (row_in_tile & 7)] = make_uint4(o[0], o[1], o[2], o[3]);
+      rowp[(2 * j + 1) ^ (row_in_tile & 7)] = make_uint4(o[4], o[5], o[6], o[7]);
     };
     uint32_t ph = 0, t = 0, c = team;
     while (c >= (uint32_t)NC && NC > 0) { c -= NC; ++t; }
@@ -189,22 +192,24 @@ channel_mix_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       const float* bias = a.b1 + c * CM_CHUNK;
       mbar_wait(&acc1_full[team], ph);
       tc_fence_after();
-      float acc[32];
-      uint32_t o[16];
-      tmem_ld_32x32(acc1_addr, acc);
+      // the chunk's 64 columns in four 16-column loads, each in flight under the GELU of the one before
+      float a0[16], a1[16];
+      tmem_ld_32x16(acc1_addr, a0);
       tmem_ld_wait();
-      gelu_pack(acc, bias, o);
+      tmem_ld_32x16(acc1_addr + 16, a1);
       mbar_wait(&h_empty[team], ph ^ 1);   // MMA2 of this team's previous chunk has retired: the hidden tile is free
-#pragma unroll
-      for (int p = 0; p < 4; ++p) rowp[p ^ (row_in_tile & 7)] = make_uint4(o[4 * p], o[4 * p + 1], o[4 * p + 2], o[4 * p + 3]);
-      tmem_ld_32x32(acc1_addr + 32, acc);
+      gelu_store(a0, bias, 0);
+      tmem_ld_wait();
+      tmem_ld_32x16(acc1_addr + 32, a0);
+      gelu_store(a1, bias + 16, 1);
+      tmem_ld_wait();
+      tmem_ld_32x16(acc1_addr + 48, a1);
+      gelu_store(a0, bias + 32, 2);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc1_empty[team]);
-      gelu_pack(acc, bias + 32, o);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) rowp[(4 + p) ^ (row_in_tile & 7)] = make_uint4(o[4 * p], o[4 * p + 1], o[4 * p + 2], o[4 * p + 3]);
+      gelu_store(a1, bias + 48, 3);
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[team]);
