@@ -207,6 +207,25 @@ struct EpiAffineResidual {
     if (out_b) st_bf4(out_b + at, v);
   }
 };
+// out += acc * alpha with fp32 reductions at L2: the epilogue of a split-K GEMM whose output already holds everything that is
+// not the product (residual + scaled bias).  The mixer's output projection at small batch is [B, 16384] x [16384, 1024]:
+// 16 output tiles for 148 SMs unless K is sliced.
+struct EpiScaledAtomicAdd {
+  static constexpr const char* name = "scaled_atomic_add";
+  static constexpr int kPrefetchDepth = 0;
+  static constexpr bool kTmaStore = false;
+  float* out;
+  int64_t ld;
+  float alpha;
+  using Regs = NoRegs;
+  using ColRegs = NoRegs;
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, int) const {}
+  __device__ __forceinline__ void load_col(int, ColRegs&) const {}
+  __device__ __forceinline__ void load(int, int, Regs&) const {}
+  __device__ __forceinline__ void frag(int row, int col, float4 acc, const Regs&, const ColRegs&) const {
+    red_add_f4(out + (int64_t)row * ld + col, make_float4(acc.x * alpha, acc.y * alpha, acc.z * alpha, acc.w * alpha));
+  }
+};
 // block output: o = acc + b2;  x_new = o (1 + s2) / nb + x_old      (mlp_flow.py:112-117)
 struct EpiBlockOut {
   static constexpr bool kNarrowTiles = true;

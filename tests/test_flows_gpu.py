@@ -55,8 +55,15 @@ def test_mixer_forward(m, D, C, nb, tm, cm, ch, B, with_lat):
                                  None if lat is None else lat.cpu().numpy().astype(np.float64),
                                  num_blocks=nb, num_channels=ch, condition_dimension=C)
     xn = x.cpu().numpy().astype(np.float64)
-    assert rel(out - xn, ref - xn) < 1e-2
+    err = rel(out - xn, ref - xn)
+    print(f"mixer block-update error vs oracle: {err:.2e}")
+    assert err < 1e-2
     assert rel(out, ref) < 1e-2
+    # run-to-run: the split-K output projection reduces with fp32 atomics, so two runs agree to rounding, not bit for bit
+    out2 = model.apply({"params": params}, x, time, lat).cpu().numpy().astype(np.float64)
+    rr = rel(out2 - xn, out - xn)
+    print(f"mixer run-to-run difference: {rr:.2e}")
+    assert rr < 2e-3
 
 
 @pytest.mark.parametrize("D,C,nb,B,with_lat", [
