@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "epilogues.cuh"
 #include "imf_layout.cuh"
+#include "convnext_mma.cuh"
 #include "mixer_fused.cuh"
 
 namespace mfac {
@@ -361,6 +362,26 @@ bool conv_dims_ok(const MfacConvDims& d) {
          d.latent_flat >= 0 && d.latent_flat % 8 == 0 && ((int64_t)d.S * d.S * d.channels) % 8 == 0;
 }
 
+// tensor-core block kernel for the reference geometry (16 channels, S = 16 or 32); other geometries keep the fp32 kernel
+template <int CH>
+bool conv_block_mma(int S, int64_t B, const float* xs, const float* film, const MfacConvBlockW& bw, __nv_bfloat16* xf, cudaStream_t s) {
+  if constexpr (CH == 16) {
+    static const bool off = getenv("MFAC_NO_CONV_MMA") != nullptr;
+    if (off || (S != 32 && S != 16)) return false;
+    static PerDeviceOnce configured;
+    if (configured.need()) {
+      cudaFuncSetAttribute(convnext_block_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convnext_mma_smem<32>());
+      cudaFuncSetAttribute(convnext_block_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convnext_mma_smem<16>());
+      configured.done();
+    }
+    if (S == 32) convnext_block_mma_kernel<32><<<(unsigned)B, 256, convnext_mma_smem<32>(), s>>>(xs, film, bw, xf);
+    else convnext_block_mma_kernel<16><<<(unsigned)B, 256, convnext_mma_smem<16>(), s>>>(xs, film, bw, xf);
+    return true;
+  } else {
+    return false;
+  }
+}
+
 template <int CH>
 int conv_forward_impl(const MfacConvDims& d, const MfacConvWeights& w, const float* x, const float* time, const float* latents,
                       float* out, int64_t B, const ConvPlan& p, cudaStream_t s) {
@@ -390,7 +411,8 @@ int conv_forward_impl(const MfacConvDims& d, const MfacConvWeights& w, const flo
     MFAC_OK(dense(p.p1, d.bottleneck, bw.input_proj2, M, SC, d.bottleneck, EpiLinearF32{bw.input_proj2.b, p.xs, SC}, s));
     // FiLM parameters                                                             (:180-181)
     MFAC_OK(dense(p.cond, d.C, bw.conditioning, M, 2 * CH, d.C, EpiLinearF32{bw.conditioning.b, p.film, 2 * CH}, s));
-    convnext_block_kernel<CH><<<(unsigned)B, 256, smem, s>>>(p.xs, p.film, bw, p.xf, d.S);
+    if (!conv_block_mma<CH>(d.S, B, p.xs, p.film, bw, p.xf, s))
+      convnext_block_kernel<CH><<<(unsigned)B, 256, smem, s>>>(p.xs, p.film, bw, p.xf, d.S);
     count_launch();
     // output projection, x / num_blocks + residual                                (:195-205)
     MFAC_OK(dense(p.xf, SC, bw.output_proj1, M, d.bottleneck, SC, EpiBiasGelu{bw.output_proj1.b, p.q1, nullptr, d.bottleneck}, s));

@@ -69,7 +69,9 @@ def test_mixer_forward(m, D, C, nb, tm, cm, ch, B, with_lat):
 @pytest.mark.parametrize("D,C,nb,B,with_lat", [
     (64, 32, 2, 5, True),        # S = 8, channels = 8
     (256, 16, 1, 3, False),      # S = 16, channels = 4
-    (1024, 128, 2, 4, True),     # S = 32, channels = 16 (the reference geometry at D = 1024)
+    (1024, 128, 2, 4, True),     # S = 32, channels = 16 (the reference geometry at D = 1024): tensor-core block kernel
+    (256, 64, 2, 3, True),       # S = 16, channels = 16: tensor-core block kernel, two m-tiles per warp
+    (1024, 64, 1, 37, False),    # S = 32, more samples than one wave of CTAs would need at small sizes, no latents
 ])
 def test_conv_forward(m, D, C, nb, B, with_lat):
     from oracle import flows_np
