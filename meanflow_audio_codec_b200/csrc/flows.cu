@@ -54,6 +54,12 @@ __global__ void add_scaled_bias_kernel(float* __restrict__ x, const float* __res
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] += bias[i % N] * alpha;
 }
+// dst[i] = bf16(gelu(src[i] + bias[i % N]))   (second half of a split-K projection whose activation needs the complete sum)
+__global__ void bias_gelu_bf16_kernel(const float* __restrict__ src, const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
+                                      int N, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(gelu_tanh(src[i] + bias[i % N]));
+}
 __global__ void copy_pair_kernel(const float* __restrict__ src, float* __restrict__ dst_f, __nv_bfloat16* __restrict__ dst_b,
                                  int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +345,7 @@ size_t convnext_smem(int S) {
 }
 
 struct ConvPlan {
-  float *x, *latc, *film, *xs;
+  float *x, *latc, *film, *xs, *q1f;
   __nv_bfloat16 *xb, *cond, *latb, *p1, *xf, *q1;
   void plan(Arena& ar, const MfacConvDims& d, int64_t B) {
     const int64_t SC = (int64_t)d.S * d.S * d.channels;
@@ -353,6 +359,7 @@ struct ConvPlan {
     xs = ar.take<float>(B * SC);
     xf = ar.take<__nv_bfloat16>(B * SC);
     q1 = ar.take<__nv_bfloat16>(B * d.bottleneck);
+    q1f = ar.take<float>(B * d.bottleneck);   // split-K partial sums of output_proj1
   }
 };
 
@@ -415,7 +422,17 @@ int conv_forward_impl(const MfacConvDims& d, const MfacConvWeights& w, const flo
       convnext_block_kernel<CH><<<(unsigned)B, 256, smem, s>>>(p.xs, p.film, bw, p.xf, d.S);
     count_launch();
     // output projection, x / num_blocks + residual                                (:195-205)
-    MFAC_OK(dense(p.xf, SC, bw.output_proj1, M, d.bottleneck, SC, EpiBiasGelu{bw.output_proj1.b, p.q1, nullptr, d.bottleneck}, s));
+    if (ceil_div(M, GEMM_BM) * ceil_div(d.bottleneck, 128) * 4 <= num_sms() && SC >= 2048 && d.bottleneck % 4 == 0) {
+      // [B, S*S*CH] x [S*S*CH, 128]: one column of tiles unless K is sliced; the GELU needs the complete sum, so the slices reduce
+      // into an fp32 scratch and a row kernel applies bias + GELU
+      MFAC_CUDA_OK(cudaMemsetAsync(p.q1f, 0, (size_t)B * d.bottleneck * 4, s));
+      MFAC_OK((launch_gemm<false, true>(GemmOperandDesc{p.xf, SC, false}, GemmOperandDesc{bw.output_proj1.w, d.bottleneck, true}, M,
+                                        d.bottleneck, SC, EpiScaledAtomicAdd{p.q1f, d.bottleneck, 1.0f}, s, 0, /*split_k=*/true)));
+      bias_gelu_bf16_kernel<<<nblk(B * d.bottleneck, 256), 256, 0, s>>>(p.q1f, bw.output_proj1.b, p.q1, d.bottleneck, B * d.bottleneck);
+      count_launch();
+    } else {
+      MFAC_OK(dense(p.xf, SC, bw.output_proj1, M, d.bottleneck, SC, EpiBiasGelu{bw.output_proj1.b, p.q1, nullptr, d.bottleneck}, s));
+    }
     MFAC_OK(dense(p.q1, d.bottleneck, bw.output_proj2, M, d.D, d.bottleneck,
                   EpiAffineResidual{bw.output_proj2.b, p.x, p.x, p.xb, d.D, inv_nb}, s));
   }
