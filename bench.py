@@ -714,6 +714,31 @@ def flows_bench(m, dev):
         out[name] = {"rows_per_s": Bf / (ms * 1e-3), "ms": ms, "batch": Bf, "blocks": CFG["num_blocks"], "D": 1024}
         del model, params, x, lat, y
         torch.cuda.empty_cache()
+        # the codec pipeline with this architecture (SURVEY.md section 8f-1 encoder wiring: MLP encoder -> latents[B, 1, L] -> the
+        # model's own latent_proj): MDCT -> encode -> 1-NFE mean-flow jump -> IMDCT on 10 s clips, device-resident
+        try:
+            clips = 16
+            cm = cls(1024, CFG["condition_dimension"], CFG["num_blocks"], CFG["latent_dimension"], num_latent_tokens=1)
+            cp = cm.init(CFG["seed"], device=dev, with_encoder=True)["params"]
+            codec = m.MeanFlowCodec(cm, cp, window_size=512, hop_size=256)
+            gg = codec.geometry(441000)
+            a = 0.1 * torch.randn(clips, gg["t_pad"], device=dev, generator=g)
+            a[:, 441000:] = 0
+            for _ in range(2):
+                yy = codec.reconstruct(a, sampler="mf", nfe=1, valid_length=441000)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                yy = codec.reconstruct(a, sampler="mf", nfe=1, valid_length=441000)
+            e1.record()
+            torch.cuda.synchronize()
+            cms = e0.elapsed_time(e1) / 3
+            out[name]["codec_mf1"] = {"clips": clips, "rows": clips * gg["rows_per_clip"], "ms": cms,
+                                      "audio_seconds_per_s": clips * 10.0 / (cms * 1e-3), "finite": bool(torch.isfinite(yy).all())}
+            del cm, cp, codec, a, yy
+        except Exception as ex:  # noqa: BLE001 -- an extra line must not cost the headline
+            out[name]["codec_mf1"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        torch.cuda.empty_cache()
     return out
 
 

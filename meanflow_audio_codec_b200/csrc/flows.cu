@@ -131,7 +131,9 @@ struct MixerPlan {
     h1 = ar.take<__nv_bfloat16>(B * (int64_t)d.channels * d.token_mix);
     t2 = ar.take<float>(B * TC);
     a2 = ar.take<__nv_bfloat16>(B * TC);
-    h2 = ar.take<__nv_bfloat16>(B * (int64_t)d.tokens * d.channel_mix);
+    // the channel-mix hidden tensor (4 MB per row at the reference widths) exists only where the fused kernel does not apply
+    h2 = ar.take<__nv_bfloat16>(channel_mix_fused_ok(d.channels, d.channel_mix) && B * (int64_t)d.tokens <= 0x7fffffff
+                                    ? 8 : B * (int64_t)d.tokens * d.channel_mix);
     u3 = ar.take<__nv_bfloat16>(B * TC);
     w2t = ar.take<__nv_bfloat16>((int64_t)d.channel_mix * d.channels);   // transposed second channel-mix kernel (fused path)
   }
@@ -369,23 +371,26 @@ bool conv_dims_ok(const MfacConvDims& d) {
          d.latent_flat >= 0 && d.latent_flat % 8 == 0 && ((int64_t)d.S * d.S * d.channels) % 8 == 0;
 }
 
-// tensor-core block kernel for the reference geometry (16 channels, S = 16 or 32); other geometries keep the fp32 kernel
+// tensor-core block kernel for the reference geometry (16 channels, S = 16 or 32); MFAC_ERR_UNSUPPORTED for the other
+// geometries, which keep the fp32 kernel
 template <int CH>
-bool conv_block_mma(int S, int64_t B, const float* xs, const float* film, const MfacConvBlockW& bw, __nv_bfloat16* xf, cudaStream_t s) {
+int conv_block_mma(int S, int64_t B, const float* xs, const float* film, const MfacConvBlockW& bw, __nv_bfloat16* xf, cudaStream_t s) {
   if constexpr (CH == 16) {
     static const bool off = getenv("MFAC_NO_CONV_MMA") != nullptr;
-    if (off || (S != 32 && S != 16)) return false;
+    if (off || (S != 32 && S != 16)) return MFAC_ERR_UNSUPPORTED;
     static PerDeviceOnce configured;
     if (configured.need()) {
-      cudaFuncSetAttribute(convnext_block_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convnext_mma_smem<32>());
-      cudaFuncSetAttribute(convnext_block_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)convnext_mma_smem<16>());
+      MFAC_CUDA_OK(cudaFuncSetAttribute(convnext_block_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)convnext_mma_smem<32>()));
+      MFAC_CUDA_OK(cudaFuncSetAttribute(convnext_block_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)convnext_mma_smem<16>()));
       configured.done();
     }
     if (S == 32) convnext_block_mma_kernel<32><<<(unsigned)B, 256, convnext_mma_smem<32>(), s>>>(xs, film, bw, xf);
     else convnext_block_mma_kernel<16><<<(unsigned)B, 256, convnext_mma_smem<16>(), s>>>(xs, film, bw, xf);
-    return true;
+    return launch_status();
   } else {
-    return false;
+    return MFAC_ERR_UNSUPPORTED;
   }
 }
 
@@ -418,8 +423,9 @@ int conv_forward_impl(const MfacConvDims& d, const MfacConvWeights& w, const flo
     MFAC_OK(dense(p.p1, d.bottleneck, bw.input_proj2, M, SC, d.bottleneck, EpiLinearF32{bw.input_proj2.b, p.xs, SC}, s));
     // FiLM parameters                                                             (:180-181)
     MFAC_OK(dense(p.cond, d.C, bw.conditioning, M, 2 * CH, d.C, EpiLinearF32{bw.conditioning.b, p.film, 2 * CH}, s));
-    if (!conv_block_mma<CH>(d.S, B, p.xs, p.film, bw, p.xf, s))
-      convnext_block_kernel<CH><<<(unsigned)B, 256, smem, s>>>(p.xs, p.film, bw, p.xf, d.S);
+    const int mma = conv_block_mma<CH>(d.S, B, p.xs, p.film, bw, p.xf, s);
+    if (mma == MFAC_ERR_UNSUPPORTED) convnext_block_kernel<CH><<<(unsigned)B, 256, smem, s>>>(p.xs, p.film, bw, p.xf, d.S);
+    else MFAC_OK(mma);
     count_launch();
     // output projection, x / num_blocks + residual                                (:195-205)
     if (ceil_div(M, GEMM_BM) * ceil_div(d.bottleneck, 128) * 4 <= num_sms() && SC >= 2048 && d.bottleneck % 4 == 0) {

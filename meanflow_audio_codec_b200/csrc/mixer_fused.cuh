@@ -260,11 +260,14 @@ __global__ void transpose_w2_kernel(const __nv_bfloat16* __restrict__ w, __nv_bf
 }
 
 // returns MFAC_ERR_UNSUPPORTED when the geometry is outside the fused kernel (the caller then runs the two GEMMs)
+// geometry the fused kernel covers (the workspace plan skips the [tokens, Hc] hidden tensor when it does)
+inline bool channel_mix_fused_ok(int CH, int Hc) {
+  static const bool off = getenv("MFAC_NO_FUSED_CHANNEL_MIX") != nullptr;
+  return !off && CH == 16 && Hc % CM_CHUNK == 0 && Hc >= CM_CHUNK && channel_mix_smem(Hc) <= 227 * 1024;
+}
 inline int channel_mix_fused(const __nv_bfloat16* a2, const MfacDense& ch1, const MfacDense& ch2, __nv_bfloat16* w2t_scratch,
                              const float* res, __nv_bfloat16* out, int64_t Mtok, int CH, int Hc, cudaStream_t s) {
-  static const bool off = getenv("MFAC_NO_FUSED_CHANNEL_MIX") != nullptr;
-  if (off || CH != 16 || Hc % CM_CHUNK != 0 || Hc < CM_CHUNK || channel_mix_smem(Hc) > 227 * 1024 || Mtok > 0x7fffffff)
-    return MFAC_ERR_UNSUPPORTED;
+  if (!channel_mix_fused_ok(CH, Hc) || Mtok > 0x7fffffff) return MFAC_ERR_UNSUPPORTED;
   transpose_w2_kernel<<<(unsigned)ceil_div(Hc * CH, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(ch2.w), w2t_scratch, Hc, CH);
   count_launch();
   CUtensorMap tmX, tmW1, tmW2t;
