@@ -646,7 +646,10 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
   // Concurrent schedule: the critical chain (block-output backward -> two dX GEMMs -> LayerNorm backward) stays on `s`; the
   // weight gradients, the remaining bias column sums and the modulation-MLP input gradient of block k run on a side stream from
   // transient set k & 1, which the critical chain only overwrites again two blocks later (after that block's side work).
-  cudaStream_t sW = conc ? fc->side[2] : s;
+  // The side work itself is three independent chains (they read g_o / g_a / g_m and write disjoint gradient slices): at small
+  // batch one side stream running five ~15 us kernels per block was the backward's critical path (80 us per block against 29 us
+  // for the chain on `s`), so the two big weight gradients get streams of their own and join sW before the block's slice is final.
+  cudaStream_t sW = conc ? fc->side[2] : s, sW1 = conc ? fc->side[3] : s, sW2 = conc ? fc->side[4] : s;
   cudaEvent_t side_done[2] = {nullptr, nullptr};
   for (int k = d.nb - 1; k >= 0; --k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
@@ -676,9 +679,9 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
     } else {
       MFAC_OK(gemm_dx(g_o, d.Dp, w + d.s_m2w, M, d.Ip, d.Dp, EpiMulDgelu{sb.a, g_a, d.Ip}, s));
     }
-    if (conc) MFAC_OK(stream_after(fc, s, sW));
-    MFAC_OK(gemm_dw(sb.hin, d.Ip, g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, sW));
-    if (!fused_colsum) MFAC_OK(colsum(g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, sW));
+    if (conc) MFAC_OK(stream_after(fc, s, sW1));
+    MFAC_OK(gemm_dw(sb.hin, d.Ip, g_a, d.Ip, d.Ip, d.Ip, M, EpiGradStore{gk + d.o_m1w, d.I, MAP_CM, 0, MAP_CM, 0, 1, d}, sW1));
+    if (!fused_colsum) MFAC_OK(colsum(g_a, d.Ip, B, gk + d.o_m1b, MAP_CM, 0, d, sW1));
     // g_hin = g_a W1^T goes out in bf16 straight into g_m[:, Ip:2Ip]: it IS the shift gradient (hin = (1+s1) n + shift)
     if (fused_colsum) {
       EpiLinearBf16Colsum ep;
@@ -690,13 +693,18 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
     phase_mark(5 + (d.nb - 1 - k), s);
-    if (conc) MFAC_OK(stream_after(fc, s, sW));
+    if (conc) {
+      MFAC_OK(stream_after(fc, s, sW));
+      MFAC_OK(stream_after(fc, s, sW2));
+    }
     MFAC_OK(gemm_dw(sb.gc, d.Ca, g_m, d.Mp, d.Cp, d.Mp, M,
-                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, sW));
+                    EpiGradStore{gk + d.o_c2w, 2 * d.I + d.D, MAP_ID, d.C, MAP_MM, 0, 1, d}, sW2));
     // s1 third (and the shift third where it was not fused above)
     MFAC_OK(colsum(g_m, d.Mp, B, gk + d.o_c2b, MAP_MM, 0, d, sW, fused_colsum ? d.Ip : 2 * d.Ip));
     MFAC_OK(gemm_dx(g_m, d.Mp, w + d.s_c2w, M, d.Cp, d.Mp, EpiMulDgelu{sb.ac, p.g_ac + k * d.Cp, d.Ca}, sW));
     if (conc) {
+      MFAC_OK(stream_after(fc, sW1, sW));
+      MFAC_OK(stream_after(fc, sW2, sW));
       side_done[par] = fc->next_event();
       MFAC_CUDA_OK(cudaEventRecord(side_done[par], sW));
     }
