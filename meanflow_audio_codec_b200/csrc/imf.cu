@@ -650,7 +650,7 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
   // batch one side stream running five ~15 us kernels per block was the backward's critical path (80 us per block against 29 us
   // for the chain on `s`), so the two big weight gradients get streams of their own and join sW before the block's slice is final.
   cudaStream_t sW = conc ? fc->side[2] : s, sW1 = conc ? fc->side[3] : s, sW2 = conc ? fc->side[4] : s;
-  cudaEvent_t side_done[2] = {nullptr, nullptr};
+  cudaEvent_t side_done[2] = {nullptr, nullptr}, g_lat_done = nullptr;
   for (int k = d.nb - 1; k >= 0; --k) {
     const __nv_bfloat16* w = sh.w + k * d.s_blk_stride;
     SavedBlock& sb = p.blk[k];
@@ -692,6 +692,10 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
     }
     LnBwdArgs lb{p.lat, x_in, sb.mu, sb.rstd, sb.m, g_m, p.g_lat, p.g_x};
     MFAC_OK(ln_bwd(lb, d, B, s));
+    if (conc && k == 0) {   // g_lat is complete: the encoder backward may start (below, on streams of its own)
+      g_lat_done = fc->next_event();
+      MFAC_CUDA_OK(cudaEventRecord(g_lat_done, s));
+    }
     phase_mark(5 + (d.nb - 1 - k), s);
     if (conc) {
       MFAC_OK(stream_after(fc, s, sW));
@@ -720,14 +724,22 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
     if (aux && aux->grad_ready && k == 0)
       for (int kk = d.nb - 1; kk >= 0; --kk) aux->grad_ready(aux->grad_ready_user, (int64_t)kk * d.blk_stride, d.blk_stride);
   }
-  // ---- encoder backward
-  f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, s>>>(p.g_lat, p.g_latb, B * d.Lp);
+  // ---- encoder backward (concurrent schedule: on two side streams beside the first-modulation-layer gradients above; it only
+  // needs g_lat, which block 0's LayerNorm backward completed)
+  cudaStream_t sE = conc ? fc->side[5] : s, sE2 = conc ? fc->side[0] : s;
+  if (conc) MFAC_CUDA_OK(cudaStreamWaitEvent(sE, g_lat_done, 0));
+  f32_to_bf16_kernel<<<blocks_for(B * d.Lp, 256), 256, 0, sE>>>(p.g_lat, p.g_latb, B * d.Lp);
   count_launch();
-  MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, 1, d}, s));
-  MFAC_OK(colsum(p.g_latb, d.Lp, B, grads + d.o_e2b, MAP_ID, d.L, d, s));
-  MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, s));
-  MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, 1, d}, s));
-  MFAC_OK(colsum(p.g_ae, d.Hep, B, grads + d.o_e1b, MAP_ID, d.He, d, s));
+  if (conc) MFAC_OK(stream_after(fc, sE, sE2));
+  MFAC_OK(gemm_dw(p.g_e, d.Hep, p.g_latb, d.Lp, d.Hep, d.Lp, M, EpiGradStore{grads + d.o_e2w, d.L, MAP_ID, d.He, MAP_ID, d.L, 1, d}, sE2));
+  MFAC_OK(colsum(p.g_latb, d.Lp, B, grads + d.o_e2b, MAP_ID, d.L, d, sE2));
+  MFAC_OK(gemm_dx(p.g_latb, d.Lp, sh.w + d.s_e2w, M, d.Hep, d.Lp, EpiMulDgelu{p.a_e, p.g_ae, d.Hep}, sE));
+  MFAC_OK(gemm_dw(p.xb, d.Dp, p.g_ae, d.Hep, d.Dp, d.Hep, M, EpiGradStore{grads + d.o_e1w, d.He, MAP_ID, d.D, MAP_ID, d.He, 1, d}, sE));
+  MFAC_OK(colsum(p.g_ae, d.Hep, B, grads + d.o_e1b, MAP_ID, d.He, d, sE));
+  if (conc) {
+    MFAC_OK(stream_after(fc, sE2, s));
+    MFAC_OK(stream_after(fc, sE, s));
+  }
   if (aux && aux->grad_ready)
     aux->grad_ready(aux->grad_ready_user, (int64_t)d.nb * d.blk_stride, d.total - (int64_t)d.nb * d.blk_stride);
   phase_mark(90, s);
