@@ -13,7 +13,7 @@ from .loss_strategies import (FlowMatchingLoss, ImprovedMeanFlowLoss, LinearNois
                               LogitNormalTimeSampling, LossStrategy, MeanFlowLoss, MeanFlowTimeSampling,
                               UniformNoiseSchedule, UniformTimeSampling, create_loss_strategy, train_step)
 from .sampling import sample, sample_mean_flow  # noqa: F401
-from .graphs import GraphedTrainStep  # noqa: F401
+from .graphs import GraphedCodec, GraphedTrainStep  # noqa: F401
 from .flows import ConditionalConvFlow, ConditionalMLPMixerFlow, create_flow_model  # noqa: F401
 from .checkpoint import load_checkpoint, save_checkpoint  # noqa: F401
 from .codec import MeanFlowCodec  # noqa: F401
