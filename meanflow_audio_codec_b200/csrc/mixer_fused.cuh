@@ -7,10 +7,11 @@
 //   warp 0      TMA: both weight matrices once per CTA (64 + 64 KB at Hc = 2048), then one [128 x CH] activation tile per tile
 //   warp 1 / 2  tcgen05.mma issuers of the first / second product (four TMEM accumulator stages, four hidden-tile stages)
 //   warps 4..19 epilogue / A-operand producers: four TEAMS of four warps (TMEM lane quarter = warp & 3); team k owns stage k of
-//               the accumulator and of the hidden tile and handles chunks k, k + 4, ...  A warp's chain per chunk (TMEM load ->
-//               GELU -> STS -> fence.proxy.async -> arrive) is ~1400 clocks of latency, so with every warp on every chunk (the
-//               first version) the kernel ran at one chunk per 1400 clocks no matter how cheap the GELU was; four chunks in
-//               flight hide it
+//               the accumulator and of the hidden tile and handles chunks k, k + 4, ..., so four chunks are in flight and a
+//               warp's TMEM-load -> GELU -> STS -> fence.proxy.async -> arrive latency chain overlaps the other teams' work
+// History (profiles/r02_channel_mix_fused.txt): the first version had ONE thread issuing both products and ran at one 64-column
+// chunk per ~1400 clocks whatever the epilogue cost (GELU removed: -4 %) -- with K = 16 per product the tensor pipe wants a new
+// instruction every few dozen clocks and ~330 SASS instructions per chunk on one thread could not supply them.
 // Both weight operands land in shared memory as [CH rows x 64 columns] 128B-swizzled boxes: W1 [CH, Hc] read as the MN-major B
 // operand of MMA1 (K = CH), the transposed copy W2^T [CH, Hc] as the K-major B operand of MMA2 (N = CH).
 #pragma once
