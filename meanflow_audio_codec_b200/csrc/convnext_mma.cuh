@@ -51,7 +51,7 @@ template <int S>
 __global__ void __launch_bounds__(256, 2) convnext_block_mma_kernel(const float* __restrict__ xs, const float* __restrict__ film,
                                                                     MfacConvBlockW w, __nv_bfloat16* __restrict__ out) {
   constexpr int CH = 16, P = S + 2, NPIX = S * S, MT = NPIX / 16, MT_W = MT / 8, TPR = S / 16;   // m-tiles, per warp, per image row
-  static_assert(S % 16 == 0 && MT % 8 == 0, "16-pixel row segments, eight warps");
+  static_assert(S % 16 == 0 && MT % 8 == 0 && NPIX % 256 == 0, "16-pixel row segments, eight warps, whole pixels per thread");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* sIn = smem_raw;                                                   // [P*P][32 B] bf16, halves swizzled, zero halo
   uint32_t* sH = reinterpret_cast<uint32_t*>(smem_raw + P * P * 32);         // [MT][8 fragment words][32 lanes] GELU'd hidden, bf16 pairs
@@ -61,6 +61,15 @@ __global__ void __launch_bounds__(256, 2) convnext_block_mma_kernel(const float*
   const int64_t b = blockIdx.x;
   const float* fb = film + b * 2 * CH;
 
+  // this thread's pixels of the input: all loads in flight before anything else (one HBM round trip, under the set-up below)
+  constexpr int PPT = NPIX / 256;
+  float4 raw[PPT][4];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const float4* src = reinterpret_cast<const float4*>(xs + (b * NPIX + tid + 256 * i) * CH);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) raw[i][c] = __ldg(src + c);
+  }
   for (int i = tid; i < P * P * 2; i += 256) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 9 * 32; i += 256) {
     const int tap = i >> 5, l = i & 31, gg = l >> 2, tt = l & 3;
@@ -73,26 +82,29 @@ __global__ void __launch_bounds__(256, 2) convnext_block_mma_kernel(const float*
   __syncthreads();
 
   // LN over channels + FiLM -> bf16 into the padded plane (the conv operand)                          (conv_flow.py:176-187)
-  for (int pix = tid; pix < NPIX; pix += 256) {
-    const float* src = xs + (b * NPIX + pix) * CH;
-    float v[CH];
+  {
+    float f1[CH], f0[CH];
 #pragma unroll
-    for (int c = 0; c < CH; c += 4) {
-      const float4 q = *reinterpret_cast<const float4*>(src + c);
-      v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+    for (int c = 0; c < CH; ++c) { f1[c] = 1.0f + fb[c]; f0[c] = fb[CH + c]; }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int pix = tid + 256 * i;
+      float v[CH];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { v[4 * c] = raw[i][c].x; v[4 * c + 1] = raw[i][c].y; v[4 * c + 2] = raw[i][c].z; v[4 * c + 3] = raw[i][c].w; }
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) { sum += v[c]; sq += v[c] * v[c]; }
+      const float mu = sum * (1.0f / CH);
+      const float rstd = rsqrtf(fmaxf(0.f, sq * (1.0f / CH) - mu * mu) + LN_EPS);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[c] = f1[c] * ((v[c] - mu) * rstd) + f0[c];
+      const int pp = ((pix / S) + 1) * P + (pix % S) + 1;
+      const int sw = (pp >> 2) & 1;
+      uint4* dst = reinterpret_cast<uint4*>(sIn + pp * 32);
+      dst[0 ^ sw] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      dst[1 ^ sw] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
     }
-    float sum = 0.f, sq = 0.f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { sum += v[c]; sq += v[c] * v[c]; }
-    const float mu = sum * (1.0f / CH);
-    const float rstd = rsqrtf(fmaxf(0.f, sq * (1.0f / CH) - mu * mu) + LN_EPS);
-#pragma unroll
-    for (int c = 0; c < CH; ++c) v[c] = (1.0f + fb[c]) * ((v[c] - mu) * rstd) + fb[CH + c];
-    const int pp = ((pix / S) + 1) * P + (pix % S) + 1;
-    const int sw = (pp >> 2) & 1;
-    uint4* dst = reinterpret_cast<uint4*>(sIn + pp * 32);
-    dst[0 ^ sw] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    dst[1 ^ sw] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
   }
   __syncthreads();
 
