@@ -644,9 +644,9 @@ def codec_bench(m, _lib, dev, pk, batches=(1, 4, 16, 64, 256, 1024, 4096), quick
                 done = 0
                 while done < Bc:
                     n = min(x_pin.shape[0], Bc - done)
-                    # sub-batches of at most 64 clips: even a 256-clip call then pipelines H2D / kernels / D2H (64 clips already
-                    # reach ~96 % of the 256-clip kernel throughput)
-                    codec.reconstruct_host(x_pin[:n], out_host=y_pin[:n], sampler=smp, nfe=nfe, key=done, sub_batch=min(SUB, 64), device=dev)
+                    # reconstruct_host picks its own sub-batch (min(64, B, 2 sqrt(B)) clips): H2D / kernels / D2H of neighbouring
+                    # sub-batches overlap, and the un-overlapped first upload / last download stay short
+                    codec.reconstruct_host(x_pin[:n], out_host=y_pin[:n], sampler=smp, nfe=nfe, key=done, sub_batch=None, device=dev)
                     done += n
 
             iters = 3 if Bc <= 256 else 1

@@ -100,10 +100,13 @@ class MeanFlowCodec:
 
     # ------------------------------------------------------------------ host buffers, streamed
     def reconstruct_host(self, audio_host: torch.Tensor, out_host: torch.Tensor | None = None, sampler: str = "mf",
-                         nfe: int = 1, key: int = 0, sub_batch: int = 256, device=None) -> torch.Tensor:
+                         nfe: int = 1, key: int = 0, sub_batch: int | None = None, device=None) -> torch.Tensor:
         """Host in, host out.  ``audio_host`` [B, T] fp32 CPU tensor (pinned for full copy/compute overlap); returns a
         pinned CPU tensor [B, out_len].  Clips are processed ``sub_batch`` at a time through two device slots per
-        direction; H2D, kernels and D2H of neighbouring sub-batches overlap on three streams."""
+        direction; H2D, kernels and D2H of neighbouring sub-batches overlap on three streams.  ``sub_batch=None`` picks
+        ``min(64, B, 2 sqrt(B))``: the first upload and the last download are not overlapped with anything, so few large chunks
+        lose to more, smaller ones until the chunks get too small for the GEMMs (measured on B200 with 10 s clips: 16 clips 80 K
+        audio-s/s at 8 per chunk against 70 K in one piece; 64 clips 108 K at 16 against 78 K at 64; 1024 clips best at 64)."""
         if audio_host.is_cuda:
             raise ValueError("audio_host must be a CPU tensor (use reconstruct() for device tensors)")
         if audio_host.ndim != 2 or audio_host.dtype != torch.float32:
@@ -113,6 +116,8 @@ class MeanFlowCodec:
         g = self.geometry(T)
         if out_host is None:
             out_host = torch.empty((B, g["out_len"]), dtype=torch.float32).pin_memory()
+        if sub_batch is None:
+            sub_batch = min(64, int(round(2.0 * B ** 0.5)))
         sb = max(1, min(int(sub_batch), B))
         compute = torch.cuda.current_stream(dev)
         up, down = self._streams(dev)
