@@ -53,7 +53,13 @@ def test_conv_param_tree_matches_reference_shapes():
 
 def test_workspace_queries_validate_geometry(lib):
     ok = _lib.MixerDims(1024, 128, 8, 1024, 16, 2048, 2048, 8192)
-    assert lib.mfac_mixer_workspace_bytes(C.byref(ok), 4) > 4 * 1024 * 2048 * 2      # holds the channel-mix hidden tensor
+    fused = lib.mfac_mixer_workspace_bytes(C.byref(ok), 4)
+    assert fused > 4 * 16 * 2048 * 2                                                  # holds the token-mix hidden tensor
+    # 16 channels + a hidden width that is a multiple of 64: the fused channel-mix kernel keeps that hidden tensor on the SM,
+    # so the plan does not carry it; a geometry outside the fused kernel (8 channels) does
+    assert fused < 4 * 1024 * 2048 * 2
+    two_gemm = _lib.MixerDims(1024, 128, 8, 1024, 8, 2048, 2048, 8192)
+    assert lib.mfac_mixer_workspace_bytes(C.byref(two_gemm), 4) > 4 * 1024 * 2048 * 2
     bad = _lib.MixerDims(1024, 128, 8, 1024, 12, 2048, 2048, 8192)                    # unsupported channel count
     assert lib.mfac_mixer_workspace_bytes(C.byref(bad), 4) == 0
     okc = _lib.ConvDims(1024, 128, 8, 32, 16, 128, 8192)
