@@ -565,27 +565,25 @@ static int loss_grad_impl(const MfacMlpDims* dims, const MfacImfConfig* cfg, con
                                        2 * d.Ip, inv_nb}, st);
   };
   if (conc_fwd) {
-    // ---- three independent forward chains side by side, then the tangent chain
-    cudaStream_t sV = fc->side[0], sS = fc->side[1];
-    Hoist hzU, hzV, hzS, hzT;   // every chain's modulation GEMMs run ahead of it on a side stream of their own
-    hzU.fc = hzV.fc = hzS.fc = hzT.fc = fc;
-    hzU.sm = hzT.sm = fc->side[3]; hzV.sm = fc->side[4]; hzS.sm = fc->side[5];
+    // ---- two independent forward chains side by side, then the tangent chain.  The saved pass of the rows with r == t (their u
+    // IS v) and the u pass of the other rows are ONE chain over all rows: cond_u = embed(t, t - r) equals cond_v = embed(t, 0) bit
+    // for bit where t - r == 0, so the rows [0, h) of cond_u already hold the (t, 0) conditioning.
+    cudaStream_t sV = fc->side[0];
+    Hoist hzU, hzV, hzT;   // every chain's modulation GEMMs run ahead of it on a side stream of their own
+    hzU.fc = hzV.fc = hzT.fc = fc;
+    hzU.sm = hzT.sm = fc->side[3]; hzV.sm = fc->side[4];
     MFAC_OK(stream_after(fc, s, sV));
-    MFAC_OK(stream_after(fc, s, sS));
-    if (Mu > 0) {   // v = f(z, [t, 0], lat) on the rows with r != t (in place on p.v, nothing kept)
+    if (Mu > 0)   // v = f(z, [t, 0], lat) on the rows with r != t (in place on p.v, nothing kept)
       MFAC_OK(forward_pass(d, sh, p.cond_v + h * d.Cp, p.lat + h * d.Lp, p.v + h * d.Dp, Mu, p.fs, sV, false, &hzV));
-      MFAC_OK(saved_pass(p.cond_u, h, Mu, Mu, s, &hzU));
-      if (tangent) {
-        // tangent of the first modulation layer (needs the primal's pre-activation ac_all, which side[3] already waits for) and
-        // the tangent modulation GEMMs of all blocks, behind the primal's modulation GEMMs on the same side stream
-        MFAC_OK(gemm_fwd(p.dcond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp,
-                         EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, hzT.sm));
-        MFAC_OK(hzT.run(hzT.sm, d.nb, tangent_mod));
-      }
+    MFAC_OK(saved_pass(p.cond_u, 0, M, M, s, &hzU));
+    if (Mu > 0 && tangent) {
+      // tangent of the first modulation layer (needs the primal's pre-activation ac_all, which side[3] already waits for) and
+      // the tangent modulation GEMMs of all blocks, behind the primal's modulation GEMMs on the same side stream
+      MFAC_OK(gemm_fwd(p.dcond_u + h * d.Cp, d.Cp, sh.w + d.s_c1all, Mu, d.Ca, d.Cp,
+                       EpiMulDgelu{p.ac_all + h * d.Ca, p.gcd + h * d.Ca, d.Ca}, hzT.sm));
+      MFAC_OK(hzT.run(hzT.sm, d.nb, tangent_mod));
     }
-    if (h > 0) MFAC_OK(saved_pass(p.cond_v, 0, (int)h, (int)h, sS, &hzS));   // rows with r == t: u IS v
     MFAC_OK(stream_after(fc, sV, s));
-    MFAC_OK(stream_after(fc, sS, s));
     if (h > 0 && aux && aux->v)
       MFAC_CUDA_OK(cudaMemcpyAsync(p.v, p.xs + (int64_t)d.nb * B * d.Dp, (size_t)h * d.Dp * 4, cudaMemcpyDeviceToDevice, s));
     phase_mark(2, s);
