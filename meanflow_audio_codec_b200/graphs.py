@@ -4,7 +4,7 @@ in ``jax.jit`` (the reference leaves it un-jitted).
     step = GraphedTrainStep(state, loss_strategy, tokenization, example_batch)
     loss = step(batch)            # batch: CUDA tensor with the example's shape; loss: 0-d CUDA tensor (static buffer)
 
-One replay = tokenise + iMF loss/grad + AdamW (+ bf16 shadow refresh): ~180-230 kernel launches (for small batches a DAG over the
+One replay = tokenise + iMF loss/grad + AdamW (+ bf16 shadow refresh): ~180-200 kernel launches (for small batches a DAG over the
 library's side streams) submitted as ONE graph launch, which is what matters at the config-faithful batch of 128 where the step is launch-bound.  The step counter
 (RNG stream offset, AdamW bias correction) lives in device memory and advances inside the graph, so consecutive
 replays draw fresh (e, t, r) exactly like consecutive eager steps with ``step=state.step``.
