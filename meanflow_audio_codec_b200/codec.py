@@ -117,7 +117,7 @@ class MeanFlowCodec:
         if out_host is None:
             out_host = torch.empty((B, g["out_len"]), dtype=torch.float32).pin_memory()
         if sub_batch is None:
-            sub_batch = min(64, int(round(2.0 * B ** 0.5)))
+            sub_batch = self.auto_sub_batch(B)
         sb = max(1, min(int(sub_batch), B))
         compute = torch.cuda.current_stream(dev)
         up, down = self._streams(dev)
@@ -158,6 +158,11 @@ class MeanFlowCodec:
         compute.wait_stream(down)
         down.synchronize()
         return out_host
+
+    @staticmethod
+    def auto_sub_batch(B: int) -> int:
+        """Clips per chunk of the host-streamed path: min(64, B, 2 sqrt(B)) (see ``reconstruct_host``)."""
+        return max(1, min(64, int(B), int(round(2.0 * float(B) ** 0.5))))
 
     _stream_cache: dict = {}
 

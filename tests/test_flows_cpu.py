@@ -164,3 +164,9 @@ def test_torch_restatement_matches_numpy_and_supports_the_loss_strategies(arch):
     out = fto(p64, z, torch.cat([tt, tt - r], -1), lat_e, **kw).sum()
     gz, gt = torch.autograd.grad(out, (z, tt))
     assert abs(float((gz * aux["v"].detach()).sum() + gt.sum()) - float(aux["dudt"].sum())) < 1e-8
+
+
+def test_codec_host_streaming_chunk_rule():
+    """MeanFlowCodec.auto_sub_batch: the measured optimum at 10 s clips (16 -> 8, 64 -> 16, 256 -> 32, >= 1024 -> 64)."""
+    f = m.MeanFlowCodec.auto_sub_batch
+    assert [f(b) for b in (1, 2, 4, 16, 64, 256, 1024, 4096)] == [1, 2, 4, 8, 16, 32, 64, 64]
